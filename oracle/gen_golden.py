@@ -1,0 +1,184 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):   python oracle/gen_golden.py
+The GPU box has no /root/reference; tests there read the committed fixtures.
+
+Shim: transformers 5.x dropped `is_torch_fx_available` and moved `rope_theta`/`rope_scaling`
+into `rope_parameters`; nothing in the reference's files is edited.  Weights are NOT sampled by torch: they come
+from `dynamic_llava_b200.synthetic.numpy_state_dict` (numpy PCG64) and are loaded strictly into the reference
+model, so a fixture stores only seeds, inputs and outputs.
+
+Forced decisions are injected without touching reference code: forward hooks on the predictor modules replace
+their logits by +/-1 patterns that make the reference's own `argsort` / `logit0 > logit1` produce the wanted mask.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+import tempfile
+
+sys.dont_write_bytecode = True
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+import torch  # noqa: E402
+import transformers.utils.import_utils as iu  # noqa: E402
+
+iu.is_torch_fx_available = lambda: False  # dynamic_modeling_llama.py:53
+
+from transformers import CLIPImageProcessor, CLIPVisionConfig, CLIPVisionModel  # noqa: E402
+from llava.model.language_model.dynamic_llava_llama import (  # noqa: E402
+    DynamicLlavaConfig,
+    DynamicLlavaLlamaForCausalLM,
+)
+
+from dynamic_llava_b200.presets import SPARSE_DEFAULTS, preset  # noqa: E402
+from dynamic_llava_b200.synthetic import forced_text_decisions, numpy_state_dict, synthetic_inputs  # noqa: E402
+
+
+class ShimCfg(DynamicLlavaConfig):
+    rope_theta = 10000.0  # read at dynamic_modeling_llama.py:368
+    rope_scaling = None  # read at :396
+
+
+def build_reference(cfg: dict, sd: dict, dtype, scratch: str):
+    vc = cfg["vision"]
+    clip_dir = os.path.join(scratch, "clip")
+    ccfg = CLIPVisionConfig(hidden_size=vc["hidden_size"], intermediate_size=vc["intermediate_size"],
+                            num_hidden_layers=vc["num_hidden_layers"], num_attention_heads=vc["num_attention_heads"],
+                            image_size=vc["image_size"], patch_size=vc["patch_size"], projection_dim=64,
+                            layer_norm_eps=vc["layer_norm_eps"], hidden_act="quick_gelu")
+    CLIPVisionModel(ccfg).save_pretrained(clip_dir)
+    CLIPImageProcessor(size={"shortest_edge": vc["image_size"]},
+                       crop_size={"height": vc["image_size"], "width": vc["image_size"]}).save_pretrained(clip_dir)
+    hcfg = ShimCfg(hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                   num_hidden_layers=cfg["num_hidden_layers"], num_attention_heads=cfg["num_attention_heads"],
+                   num_key_value_heads=cfg["num_attention_heads"], vocab_size=cfg["vocab_size"],
+                   rms_norm_eps=cfg["rms_norm_eps"], max_position_embeddings=cfg["max_position_embeddings"],
+                   pretraining_tp=1, sparse_config=copy.deepcopy(cfg["sparse_config"]),
+                   mm_vision_tower=clip_dir, mm_projector_type="mlp2x_gelu", mm_hidden_size=cfg["mm_hidden_size"],
+                   mm_vision_select_layer=cfg["mm_vision_select_layer"], mm_vision_select_feature="patch",
+                   mm_patch_merge_type="flat", use_cache=True, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+    model = DynamicLlavaLlamaForCausalLM(hcfg).eval()
+    model.get_vision_tower().load_model()
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    # rotary inv_freq / cos / sin are non-persistent buffers; nothing else may be missing
+    assert not unexpected, unexpected
+    assert all("rotary_emb" in m or "position_ids" in m for m in missing), missing
+    model.to(dtype)
+    return model
+
+
+def force_hooks(model, keep_index=None, decisions=None):
+    """decisions: iterator yielding bool[B] per decode call."""
+    handles = []
+    if keep_index is not None:
+        def vis_hook(mod, args, out):
+            z = torch.zeros_like(out)
+            z[..., 0] = -1.0
+            z[..., 0].scatter_(1, keep_index, 1.0)
+            return z
+        handles.append(model.model.image_score_predictor.register_forward_hook(vis_hook))
+    if decisions is not None:
+        it = iter(decisions)
+
+        def txt_hook(mod, args, out):
+            d = next(it)
+            z = torch.zeros_like(out)
+            z[..., 0] = torch.where(d.reshape(-1, 1), 1.0, -1.0).to(out.dtype)
+            return z
+        handles.append(model.model.output_text_score_predictor.register_forward_hook(txt_hook))
+    return handles
+
+
+@torch.no_grad()
+def run_reference(model, input_ids, pixels, n_new, forced_dec=None, forced_keep=None, capture_layers=False):
+    """Loop shape of llava/dynamic_eval/model_lvis_for_meteor.py:145-174 (batched like
+    bench_test/dynamic_llava_long_text_mem.py:310-338)."""
+    cap = {}
+    hs = []
+    hs.append(model.model.image_score_predictor.register_forward_hook(
+        lambda m, a, o: cap.setdefault("vision_logits", o.detach().clone())))
+    if hasattr(model.model, "output_text_score_predictor"):
+        cap["text_logits"] = []
+        hs.append(model.model.output_text_score_predictor.register_forward_hook(
+            lambda m, a, o: cap["text_logits"].append(o.detach().clone())))
+    if capture_layers:
+        cap["layer_inputs"] = []
+        for layer in model.model.layers:
+            hs.append(layer.register_forward_pre_hook(
+                lambda m, a, kw: cap["layer_inputs"].append((a[0] if a else kw["hidden_states"]).detach().clone()),
+                with_kwargs=True))
+    hs += force_hooks(model, forced_keep, None if forced_dec is None else list(forced_dec))
+    ids, past, images = input_ids, None, pixels
+    toks, lgs, tls = [], [], []
+    prefill_layers = None
+    for t in range(n_new):
+        out = model(ids, images=images, past_key_values=past)
+        if t == 0 and capture_layers:
+            prefill_layers = cap["layer_inputs"]
+            cap["layer_inputs"] = []
+        images = None
+        last = out.logits[:, -1, :]
+        nxt = torch.argmax(last, dim=-1)
+        toks.append(nxt)
+        lgs.append(last.clone())
+        past = out.past_key_values
+        tls.append(torch.stack([x.clone() for x in past[1]], 0))
+        ids = nxt.reshape(-1, 1)
+    for h in hs:
+        h.remove()
+    res = {
+        "tokens": torch.stack(toks, 1),
+        "logits": torch.stack(lgs, 0),
+        "true_len_hist": torch.stack(tls, 0),
+        "vision_logits": cap["vision_logits"],
+        "kv_shapes": torch.tensor([k.shape[-2] for (k, v) in past[0]]),
+        "k_last": [k.clone() for (k, v) in past[0]],
+        "v_last": [v.clone() for (k, v) in past[0]],
+    }
+    if cap.get("text_logits"):
+        res["text_logits"] = torch.stack(cap["text_logits"], 0)
+    if prefill_layers is not None:
+        res["prefill_layer_inputs"] = prefill_layers
+    return res
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    torch.set_num_threads(8)
+    cfg = preset("toy")
+    cases = [
+        # name, dtype, B, T, n_new, forced decisions?, output predictor on?
+        ("toy_fp32_b1_natural", torch.float32, 1, 12, 8, False, True),
+        ("toy_fp32_b2_natural", torch.float32, 2, 12, 8, False, True),
+        ("toy_bf16_b1_natural", torch.bfloat16, 1, 12, 8, False, True),
+        ("toy_bf16_b1_forced", torch.bfloat16, 1, 12, 12, True, True),
+        ("toy_bf16_b2_forced", torch.bfloat16, 2, 12, 12, True, True),
+        ("toy_bf16_b3_nodrop", torch.bfloat16, 3, 16, 6, False, False),
+    ]
+    with tempfile.TemporaryDirectory(dir=os.path.join(ROOT, "oracle")) as scratch:
+        for name, dtype, B, T, n_new, forced, out_pred in cases:
+            c = copy.deepcopy(cfg)
+            sd = numpy_state_dict(c, seed=0)
+            c["sparse_config"]["use_output_text_predictor"] = True  # module must exist to load every key
+            model = build_reference(c, sd, dtype, scratch)
+            model.model.config.sparse_config["use_output_text_predictor"] = out_pred  # runtime flag, like the bench script
+            ids, pix = synthetic_inputs(c, B, T, seed=1, dtype=dtype)
+            fd = forced_text_decisions(n_new - 1, B, keep_rate=[0.3, 0.7, 0.5][:B] if B > 1 else 0.5, seed=3) if forced else None
+            res = run_reference(model, ids, pix, n_new, forced_dec=fd, capture_layers=(name == "toy_bf16_b1_natural"))
+            res.update(name=name, dtype=str(dtype), B=B, T=T, n_new=n_new, weight_seed=0, input_seed=1,
+                       forced_decisions=fd, use_output_text_predictor=out_pred, preset="toy",
+                       torch_version=torch.__version__)
+            if name != "toy_bf16_b2_forced":  # keep the repo small: KV dumps only where a test reads them
+                res.pop("k_last"), res.pop("v_last")
+            torch.save(res, os.path.join(out_dir, name + ".pt"))
+            print(name, "tokens", res["tokens"].tolist(), "kv", res["kv_shapes"].tolist(),
+                  "true_len", res["true_len_hist"][-1].tolist())
+
+
+if __name__ == "__main__":
+    main()

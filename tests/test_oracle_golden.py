@@ -1,0 +1,98 @@
+"""Pin the CPU oracle (oracle/dynllava_oracle.py) against vectors produced by the UNMODIFIED reference
+(oracle/gen_golden.py, run in the build container).  Same torch, same CPU kernels, same op order -> bit-exact."""
+import copy
+import glob
+import os
+
+import pytest
+import torch
+
+from dynamic_llava_b200.presets import preset
+from dynamic_llava_b200.synthetic import numpy_state_dict, synthetic_inputs
+from oracle import dynllava_oracle as O
+
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "toy_*.pt")))
+DT = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}
+
+
+def _load(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    cfg = preset(g["preset"])
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    dt = DT[g["dtype"]]
+    sd = {k: v.to(dt) for k, v in numpy_state_dict(cfg, seed=g["weight_seed"]).items()}
+    cfg["sparse_config"]["use_output_text_predictor"] = g["use_output_text_predictor"]
+    ids, pix = synthetic_inputs(cfg, g["B"], g["T"], seed=g["input_seed"], dtype=dt)
+    return g, cfg, sd, ids, pix
+
+
+def test_fixtures_present():
+    assert len(CASES) >= 6
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_bitexact(golden_dir, name):
+    g, cfg, sd, ids, pix = _load(golden_dir, name)
+    torch.set_num_threads(8)
+    res = O.greedy_loop(sd, cfg, ids, pix, g["n_new"], forced_text_decisions=g["forced_decisions"])
+    assert torch.equal(res["tokens"], g["tokens"])
+    assert torch.equal(res["logits"], g["logits"]), (res["logits"] - g["logits"]).abs().max()
+    assert torch.equal(res["true_len"], g["true_len_hist"][-1])
+    kv_shapes = torch.tensor([k.shape[-2] for (k, v) in res["past"][0]])
+    assert torch.equal(kv_shapes, g["kv_shapes"])
+    if "k_last" in g:
+        for l, (k, v) in enumerate(res["past"][0]):
+            assert torch.equal(k, g["k_last"][l]) and torch.equal(v, g["v_last"][l])
+
+
+def test_vision_logits_and_layer_inputs(golden_dir):
+    g, cfg, sd, ids, pix = _load(golden_dir, "toy_bf16_b1_natural")
+    rec = {}
+    O.model_forward(sd, cfg, ids, images=pix, record=rec)
+    assert torch.equal(rec["vision_logits"], g["vision_logits"])
+    assert len(rec["layer_inputs"]) == len(g["prefill_layer_inputs"])
+    for a, b in zip(rec["layer_inputs"], g["prefill_layer_inputs"]):
+        assert torch.equal(a, b)
+    # fact 2: layers 0-1 see all P tokens, layers >= 2 only the kept ones
+    P = g["T"] - 1 + 16
+    assert rec["layer_inputs"][0].shape[1] == P and rec["layer_inputs"][2].shape[1] == P - 16 + 8
+    # fact 8: RoPE positions are the original (pre-drop) positions
+    pos = rec["position_ids"][0]
+    assert pos[:5].tolist() == list(range(5)) and pos[-6:].tolist() == list(range(P - 6, P))
+    assert torch.equal(pos[5:13], rec["keep_index"][0] + 5)
+
+
+def test_forced_decisions_realised(golden_dir):
+    g, cfg, sd, ids, pix = _load(golden_dir, "toy_bf16_b2_forced")
+    fd = g["forced_decisions"]
+    P = g["T"] - 1 + 16
+    # layers 0-1 always append (fact 4); layers >= 2 append iff decided
+    assert g["true_len_hist"][-1][0].tolist() == [P + g["n_new"] - 1] * 2
+    assert g["true_len_hist"][-1][2].tolist() == (P - 8 + fd.sum(0)).tolist()
+
+
+def test_batched_quirk_differs_from_per_sample(golden_dir):
+    """for B>1 with dropping, the reference's zero-padded cache changes the logits of the shorter sample;
+    per-sample (B==1) semantics are the clean target.  Both oracles must exist and must differ here."""
+    g, cfg, sd, ids, pix = _load(golden_dir, "toy_bf16_b2_forced")
+    kw = dict(forced_text_decisions=g["forced_decisions"], teacher_tokens=g["tokens"])
+    batched = O.greedy_loop(sd, cfg, ids, pix, g["n_new"], **kw)
+    single = O.greedy_loop(sd, cfg, ids, pix, g["n_new"], per_sample=True, **kw)
+    assert torch.equal(batched["logits"], g["logits"])
+    assert torch.equal(single["true_len"], batched["true_len"])
+    d = (batched["logits"] - single["logits"]).abs().amax(dim=(0, 2))
+    assert d.max() > 1e-2  # the quirk is visible
+    # prefill has no padding: B=2 vs B=1 differ only by bf16 GEMM blocking noise (measured ~0.06 on |logit|~10)
+    assert (single["logits"][0] - batched["logits"][0]).abs().max() < 0.02 * batched["logits"][0].abs().max()
+    # ...while the sample that dropped tokens next to a longer batch-mate deviates far more once padding appears
+    assert d.max() > 3 * (single["logits"][0] - batched["logits"][0]).abs().max()
+
+
+def test_hf_greedy_generate_semantics(golden_dir):
+    g, cfg, sd, ids, pix = _load(golden_dir, "toy_bf16_b3_nodrop")
+    out = O.hf_greedy_generate(sd, cfg, ids, pix, max_new_tokens=g["n_new"], eos_token_id=None)
+    assert torch.equal(out, g["tokens"])
+    eos = int(g["tokens"][1, 2])
+    out = O.hf_greedy_generate(sd, cfg, ids, pix, max_new_tokens=g["n_new"], eos_token_id=eos, pad_token_id=0)
+    assert out[1, 2] == eos and (out[1, 3:] == 0).all()
+    assert torch.equal(out[0], g["tokens"][0][: out.shape[1]])
