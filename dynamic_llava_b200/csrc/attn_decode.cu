@@ -1,0 +1,260 @@
+// K3: ragged split-KV decode attention (q_len == 1) over the KV arena [B, heads, cap, 128].
+// Reference: DynamicLlamaSdpaAttention with q_len == 1 (dynamic_modeling_llama.py:1061-1122): the new token attends to
+// cache ++ itself, unmasked, scale 1/sqrt(128), fp32 softmax; whether its k/v are persisted is decided elsewhere.
+//
+// HBM-bound (bytes = len * 2 * 128 * 2 per (sample, head)); tensor cores have nothing to do at one query row per head.
+// One CTA per (head, sample, split): a producer warp streams 64-key K and V tiles (16 KB each, contiguous in the arena)
+// with 1-D TMA bulk copies into a 3-stage shared-memory ring guarded by mbarriers; four consumer warps each own 16 keys
+// of a tile and keep a private online-softmax state, merged once at the end.  Per-sample lengths come from the device
+// (`kv_len`), so a decode step needs no host sync and is CUDA-graph replayable; CTAs whose split is empty exit early.
+//
+// `quirk_pad` reproduces the reference's B>1 batching artefact: every layer's cache is zero-padded to
+// the batch maximum and the pad is NOT masked, i.e. (max_b len - len_b) extra keys with score 0 and value 0.
+#include "common.cuh"
+#include "../../include/dynllava_b200.h"
+
+#define AD_HD 128
+#define AD_TK 64
+#define AD_STAGES 3
+#define AD_CWARPS 4
+#define AD_THREADS ((AD_CWARPS + 1) * 32)
+#define AD_STAGE_BYTES (2 * AD_TK * AD_HD * 2)
+
+struct AdSmem {
+  alignas(128) bf16 kv[AD_STAGES][2][AD_TK * AD_HD];  // [stage][K|V][key][dim]
+  alignas(8) uint64_t full[AD_STAGES];
+  alignas(8) uint64_t empty[AD_STAGES];
+  float m[AD_CWARPS], l[AD_CWARPS];
+  float acc[AD_CWARPS][AD_HD];
+};
+
+__global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
+    const bf16* __restrict__ q, int q_row_stride,  // q[b] at q + b*q_row_stride, [heads*128]
+    const bf16* __restrict__ k_arena, const bf16* __restrict__ v_arena, const bf16* __restrict__ k_side,
+    const bf16* __restrict__ v_side, const int32_t* __restrict__ kv_len, bf16* __restrict__ out, float* __restrict__ ws_acc,
+    float* __restrict__ ws_ml, int B, int heads, int cap, int n_split, float scale, int quirk_pad) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  AdSmem& S = *reinterpret_cast<AdSmem*>(smem_raw);
+  const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = kv_len[b];
+  int kps = (len + n_split - 1) / n_split;
+  kps = ((kps + AD_TK - 1) / AD_TK) * AD_TK;
+  const int k0 = split * kps;
+  const int k1 = min(len, k0 + kps);
+  const int n_keys = max(k1 - k0, 0);
+  const int n_tiles = (n_keys + AD_TK - 1) / AD_TK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AD_STAGES; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], AD_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const bf16* kbase = k_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
+  const bf16* vbase = v_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
+
+  if (warp == AD_CWARPS) {
+    // ---------------- producer warp: TMA bulk copies ----------------
+    if (lane == 0) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % AD_STAGES;
+        const uint32_t ph = (t / AD_STAGES) & 1;
+        mbar_wait(&S.empty[s], ph ^ 1);
+        const int keys = min(AD_TK, n_keys - t * AD_TK);
+        const uint32_t bytes = keys * AD_HD * 2;
+        mbar_expect_tx(&S.full[s], 2 * bytes);
+        tma_bulk_g2s(S.kv[s][0], kbase + (int64_t)t * AD_TK * AD_HD, bytes, &S.full[s]);
+        tma_bulk_g2s(S.kv[s][1], vbase + (int64_t)t * AD_TK * AD_HD, bytes, &S.full[s]);
+      }
+    }
+  } else {
+    // ---------------- consumer warps ----------------
+    const int cidx = lane & 15, sub = lane >> 4;
+    float qf[8];
+    unpack8(ld8(q + (int64_t)b * q_row_stride + h * AD_HD + cidx * 8), qf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qf[e] *= scale;
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % AD_STAGES;
+      const uint32_t ph = (t / AD_STAGES) & 1;
+      mbar_wait(&S.full[s], ph);
+      const int keys = min(AD_TK, n_keys - t * AD_TK);
+      const int wk0 = warp * 16;  // first key of this warp inside the tile
+      if (wk0 < keys) {
+        const bf16* Ks = S.kv[s][0];
+        const bf16* Vs = S.kv[s][1];
+        float sc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kk = wk0 + 2 * i + sub;
+          float kf[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(Ks + kk * AD_HD + cidx * 8), kf);
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d += qf[e] * kf[e];
+          d += __shfl_xor_sync(0xffffffffu, d, 8);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          sc[i] = (kk < keys) ? d : -INFINITY;
+        }
+        float mt = sc[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mt = fmaxf(mt, sc[i]);
+        mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+        const float m_new = fmaxf(m_run, mt);  // finite: key wk0 is valid
+        const float alpha = __expf(m_run - m_new);
+        float pm[8], po[8], ls = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pm[i] = __expf(sc[i] - m_new);
+          ls += pm[i];
+        }
+        ls += __shfl_xor_sync(0xffffffffu, ls, 16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) po[i] = __shfl_xor_sync(0xffffffffu, pm[i], 16);
+        l_run = l_run * alpha + ls;
+        m_run = m_new;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] *= alpha;
+        const int nk = min(16, keys - wk0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int kk = 2 * i + u;
+            if (kk < nk) {
+              const float p = (u == sub) ? pm[i] : po[i];
+              const uint2 raw = *reinterpret_cast<const uint2*>(Vs + (wk0 + kk) * AD_HD + lane * 4);
+              const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+              const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+              acc[0] += p * v01.x;
+              acc[1] += p * v01.y;
+              acc[2] += p * v23.x;
+              acc[3] += p * v23.y;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.empty[s]);
+    }
+
+    // the new token itself (side buffer); handled once, by warp 0 of split 0
+    if (warp == 0 && split == 0 && k_side != nullptr) {
+      float d = 0.f;
+      if (sub == 0) {
+        float kf[8];
+        unpack8(ld8(k_side + ((int64_t)b * heads + h) * AD_HD + cidx * 8), kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d += qf[e] * kf[e];
+      }
+      d += __shfl_xor_sync(0xffffffffu, d, 8);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d = __shfl_sync(0xffffffffu, d, 0);
+      const float m_new = fmaxf(m_run, d);
+      const float alpha = __expf(m_run - m_new);
+      const float p = __expf(d - m_new);
+      const uint2 raw = *reinterpret_cast<const uint2*>(v_side + ((int64_t)b * heads + h) * AD_HD + lane * 4);
+      const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      acc[0] = acc[0] * alpha + p * v01.x;
+      acc[1] = acc[1] * alpha + p * v01.y;
+      acc[2] = acc[2] * alpha + p * v23.x;
+      acc[3] = acc[3] * alpha + p * v23.y;
+      l_run = l_run * alpha + p;
+      m_run = m_new;
+    }
+    if (lane == 0) {
+      S.m[warp] = m_run;
+      S.l[warp] = l_run;
+    }
+    *reinterpret_cast<float4*>(&S.acc[warp][lane * 4]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+  __syncthreads();
+
+  // ---------------- merge the four warp states (+ the zero-pad pseudo keys) ----------------
+  if (threadIdx.x < AD_HD) {
+    const int d = threadIdx.x;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < AD_CWARPS; ++w) M = fmaxf(M, S.m[w]);
+    int n_pad = 0;
+    if (quirk_pad && split == 0) {
+      int mx = 0;
+      for (int i = 0; i < B; ++i) mx = max(mx, kv_len[i]);
+      n_pad = mx - len;
+      if (n_pad > 0) M = fmaxf(M, 0.f);
+    }
+    float L = 0.f, O = 0.f;
+    if (M > -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < AD_CWARPS; ++w) {
+        const float f = (S.m[w] > -INFINITY) ? __expf(S.m[w] - M) : 0.f;
+        L += S.l[w] * f;
+        O += S.acc[w][d] * f;
+      }
+      if (n_pad > 0) L += (float)n_pad * __expf(0.f - M);
+    }
+    if (n_split == 1) {
+      out[(int64_t)b * heads * AD_HD + h * AD_HD + d] = f2bf(O / L);
+    } else {
+      const int64_t slot = ((int64_t)b * heads + h) * n_split + split;
+      ws_acc[slot * AD_HD + d] = O;
+      if (d == 0) {
+        ws_ml[slot * 2] = M;
+        ws_ml[slot * 2 + 1] = L;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AD_HD) attn_decode_combine_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml,
+                                                                    bf16* __restrict__ out, int heads, int n_split) {
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const int64_t base = ((int64_t)b * heads + h) * n_split;
+  float M = -INFINITY;
+  for (int s = 0; s < n_split; ++s) M = fmaxf(M, ws_ml[(base + s) * 2]);
+  float L = 0.f, O = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float m = ws_ml[(base + s) * 2];
+    const float f = (m > -INFINITY) ? __expf(m - M) : 0.f;
+    L += ws_ml[(base + s) * 2 + 1] * f;
+    O += ws_acc[(base + s) * AD_HD + d] * f;
+  }
+  out[(int64_t)b * heads * AD_HD + h * AD_HD + d] = f2bf(O / L);
+}
+
+extern "C" int64_t dl_attn_decode_workspace_bytes(int B, int heads, int n_split) {
+  return n_split <= 1 ? 0 : (int64_t)B * heads * n_split * (AD_HD + 2) * (int64_t)sizeof(float);
+}
+
+extern "C" int dl_attn_decode(const void* q, int q_row_stride, const void* k_arena, const void* v_arena, const void* k_side,
+                              const void* v_side, const int32_t* kv_len, void* out, void* workspace, int B, int heads,
+                              int head_dim, int cap, int n_split, float scale, int quirk_pad, cudaStream_t stream) {
+  DL_REQUIRE(head_dim == AD_HD && n_split >= 1 && (n_split == 1 || workspace != nullptr), "dl_attn_decode");
+  if (B == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem));
+    if (e != cudaSuccess) return dl_set_error((int)e, "dl_attn_decode(smem attr)");
+    attr_set = true;
+  }
+  float* ws_acc = (float*)workspace;
+  float* ws_ml = ws_acc ? ws_acc + (int64_t)B * heads * n_split * AD_HD : nullptr;
+  attn_decode_kernel<<<dim3(heads, B, n_split), AD_THREADS, sizeof(AdSmem), stream>>>(
+      (const bf16*)q, q_row_stride, (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)k_side, (const bf16*)v_side,
+      kv_len, (bf16*)out, ws_acc, ws_ml, B, heads, cap, n_split, scale, quirk_pad);
+  if (n_split > 1)
+    attn_decode_combine_kernel<<<dim3(heads, B), AD_HD, 0, stream>>>(ws_acc, ws_ml, (bf16*)out, heads, n_split);
+  DL_CHECK_LAUNCH("dl_attn_decode");
+}

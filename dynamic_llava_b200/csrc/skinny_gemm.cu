@@ -1,0 +1,193 @@
+// Weight-streaming "skinny" GEMM for the decode step:  Y[M, N] = X[M, K] . W[N, K]^T  with M = batch <= 64.
+// (every nn.Linear of the decoder at q_len == 1: dynamic_modeling_llama.py:1011-1013, :1127, :328, :2709.)
+//
+// At M <= 64 the op is bound by reading W once from HBM (13.5 GB per 7B decode step), so the kernel is built as a
+// streaming engine: a TMA producer warp pulls 128-row x 64-col W tiles (16 KB, 128B-swizzled) plus the matching X tile
+// through a 5-stage mbarrier ring; ONE elected thread issues tcgen05.mma (A = W tile from smem, B = X tile from smem,
+// D = 128 x NB fp32 accumulator in TMEM, NB = batch padded to 16/32/64); four epilogue warps read TMEM with tcgen05.ld.
+// No weight byte ever passes through registers or the LSU.  Split-K across blockIdx.y fills the 148 SMs for the
+// narrow-N projections; every split writes its own fp32 slice partial[split][m][n] (no atomics -> deterministic), and
+// the fused consumer kernels in decode_fused.cu sum the slices in fixed order.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "../../include/dynllava_b200.h"
+
+#define SG_BM 128
+#define SG_BK 64
+#define SG_STAGES 5
+#define SG_THREADS 192  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+template <int NB>
+struct SgSmem {
+  alignas(1024) bf16 a[SG_STAGES][SG_BM * SG_BK];
+  alignas(1024) bf16 b[SG_STAGES][(NB < 8 ? 8 : NB) * SG_BK];
+  alignas(8) uint64_t full[SG_STAGES];
+  alignas(8) uint64_t empty[SG_STAGES];
+  alignas(8) uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                                                                 const __grid_constant__ CUtensorMap tmap_x,
+                                                                 float* __restrict__ partial, int M, int N, int KB,
+                                                                 int kb_per_split) {
+  constexpr int TM_COLS = NB < 32 ? 32 : NB;
+  extern __shared__ uint8_t smem_raw[];
+  SgSmem<NB>& S = *reinterpret_cast<SgSmem<NB>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * SG_BM;
+  const int split = blockIdx.y;
+  const int kb0 = split * kb_per_split;
+  const int kb1 = min(KB, kb0 + kb_per_split);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < SG_STAGES; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    mbar_init(&S.tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TM_COLS>(&S.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t BYTES = (SG_BM + NB) * SG_BK * 2;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % SG_STAGES;
+        const uint32_t ph = (i / SG_STAGES) & 1;
+        mbar_wait(&S.empty[s], ph ^ 1);
+        mbar_expect_tx(&S.full[s], BYTES);
+        tma_load_2d(S.a[s], &tmap_w, (kb0 + i) * SG_BK, n0, &S.full[s]);
+        tma_load_2d(S.b[s], &tmap_x, (kb0 + i) * SG_BK, 0, &S.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(SG_BM, NB);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % SG_STAGES;
+        const uint32_t ph = (i / SG_STAGES) & 1;
+        mbar_wait(&S.full[s], ph);
+        tc_fence_after();
+        const uint64_t da = umma_desc_kmajor_sw128(smem_u32(S.a[s]));
+        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(S.b[s]));
+#pragma unroll
+        for (int k = 0; k < SG_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle atom (encoded >> 4)
+          umma_bf16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&S.empty[s]);  // smem slot reusable once these MMAs have read it
+      }
+      umma_commit(&S.tmem_full);
+    }
+  } else {
+    // epilogue: TMEM lane = W row inside the tile, TMEM column = batch row m
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int n = n0 + q * 32 + lane;
+    float* dst = partial + (int64_t)split * M * N + n;
+    if (nkb > 0) {
+      mbar_wait(&S.tmem_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < NB; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
+        tmem_ld_wait();
+        if (n < N) {
+#pragma unroll
+          for (int m = 0; m < 16; ++m)
+            if (c0 + m < M) dst[(int64_t)(c0 + m) * N] = __uint_as_float(r[m]);
+        }
+      }
+    } else if (n < N) {
+      for (int m = 0; m < M; ++m) dst[(int64_t)m * N] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TM_COLS>(tmem_d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps (driver entry point resolved at run time: the .so must load on a CPU-only box)
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle
+extern "C" int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                               uint32_t box_rows, uint32_t box_cols) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  if (enc == nullptr) return dl_set_error(-2, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dl_set_error((int)r, "cuTensorMapEncodeTiled");
+  return 0;
+}
+
+template <int NB>
+static int launch_sg(const CUtensorMap& tw, const CUtensorMap& tx, float* partial, int M, int N, int KB, int splits, int kbps,
+                     cudaStream_t stream) {
+  const int smem = (int)sizeof(SgSmem<NB>) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return dl_set_error((int)e, "dl_skinny_gemm(smem attr)");
+    attr_set = true;
+  }
+  dim3 grid((N + SG_BM - 1) / SG_BM, splits);
+  skinny_gemm_kernel<NB><<<grid, SG_THREADS, smem, stream>>>(tw, tx, partial, M, N, KB, kbps);
+  DL_CHECK_LAUNCH("dl_skinny_gemm");
+}
+
+extern "C" int dl_skinny_gemm_splits(int N, int K, int target_ctas) {
+  const int tiles = (N + SG_BM - 1) / SG_BM;
+  const int KB = K / SG_BK;
+  int s = (target_ctas + tiles / 2) / tiles;
+  if (s < 1) s = 1;
+  int max_s = KB / 4;  // keep >= 4 k-blocks (64 KB of W) per CTA
+  if (max_s < 1) max_s = 1;
+  if (s > max_s) s = max_s;
+  const int kbps = (KB + s - 1) / s;
+  return (KB + kbps - 1) / kbps;  // effective number of non-empty splits
+}
+
+extern "C" int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits,
+                              cudaStream_t stream) {
+  DL_REQUIRE(M >= 1 && M <= 64 && K % SG_BK == 0 && N % 8 == 0 && splits >= 1, "dl_skinny_gemm");
+  const int KB = K / SG_BK;
+  const int kbps = (KB + splits - 1) / splits;
+  DL_REQUIRE((splits - 1) * kbps < KB, "dl_skinny_gemm(empty split)");
+  const int NB = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  alignas(64) CUtensorMap tw, tx;
+  int rc = dl_make_tmap_2d(&tw, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, SG_BM, SG_BK);
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)K, (uint32_t)NB, SG_BK);
+  if (rc) return rc;
+  if (NB == 16) return launch_sg<16>(tw, tx, partial, M, N, KB, splits, kbps, stream);
+  if (NB == 32) return launch_sg<32>(tw, tx, partial, M, N, KB, splits, kbps, stream);
+  return launch_sg<64>(tw, tx, partial, M, N, KB, splits, kbps, stream);
+}

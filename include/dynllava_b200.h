@@ -1,0 +1,140 @@
+/* dynllava_b200.h — C ABI of libdynllava_b200.so (hand-written sm_100a kernels for Dynamic-LLaVA's sparsified
+ * prefill/decode path).
+ *
+ * The reference (Osilly/dynamic_llava @ e1469bc) has no FFI/plugin boundary — it is pure PyTorch — so these entry points
+ * are what a PyTorch-side binding of that path would call (ctypes stub in INTEGRATION.md); each one names the reference
+ * code it replaces (paths relative to llava/model/; DML = language_model/dynamic_modeling_llama.py,
+ * CU = language_model/cache_utils.py, ARCH = dynamic_llava_arch.py, CTL = language_model/custom_transformer_layer.py).
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (kernels never allocate or free); tensors are
+ * bf16 unless stated; all calls are asynchronous on `stream`; return 0 on success, a cudaError_t value (>0) or a
+ * negative argument error otherwise; dl_last_error_string() describes the last failure on the calling thread.
+ * Nothing here synchronises with the host, so any sequence of calls can be captured into a CUDA graph.
+ */
+#ifndef DYNLLAVA_B200_H
+#define DYNLLAVA_B200_H
+
+#include <cuda_runtime_api.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DL_B200_ABI_VERSION 1
+
+int dl_version(void);
+const char* dl_last_error_string(void);
+int dl_device_is_sm100(void);
+int dl_set_error(int code, const char* where); /* internal */
+
+/* ---- K4: row kernels ------------------------------------------------------------------------------------------ */
+/* LlamaRMSNorm.forward, DML:134-139.  x,y [rows,H]; w [H]. */
+int dl_rmsnorm(const void* x, const void* w, void* y, int rows, int H, float eps, cudaStream_t stream);
+/* nn.LayerNorm in the predictors (DML:1325, :1375; CTL:293,308) and HF CLIP (pre_layrnorm, layer_norm1/2). */
+int dl_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int H, float eps, cudaStream_t stream);
+/* LlamaMLP: act_fn(gate) * up, DML:328.  gate_up [rows, 2I] = [gate | up]; out [rows, I]. */
+int dl_swiglu(const void* gate_up, void* out, int64_t rows, int I, cudaStream_t stream);
+/* optional bias + activation in place.  act 0: none, 1: nn.GELU (erf) (DML:1327,1341,1343; CTL:94; projector GELU),
+ * 2: quick_gelu (HF CLIP MLP). */
+int dl_bias_act(void* x, const void* bias, int64_t rows, int N, int act, cudaStream_t stream);
+/* residual x += y (DML:1289,1295; CTL:321-322; HF CLIPEncoderLayer). */
+int dl_add(void* x, const void* y, int64_t n, cudaStream_t stream);
+
+/* ---- multimodal splice: prepare_inputs_labels_for_multimodal, ARCH:364-405, :509-579 -------------------------- */
+/* ids int64 [B,T]; seq_len int32 [B] (#ids per sample); img_pos int32 [B] (index of the -200 id, <0: none);
+ * table [V,H]; image_feat [B,n_img,H]; out [B,P,H], P = max_b(seq_len-1+n_img); rows past a sample's end are zeroed. */
+int dl_embed_splice(const int64_t* ids, const int32_t* seq_len, const int32_t* img_pos, const void* table,
+                    const void* image_feat, void* out, int B, int T, int P, int n_img, int H, int V, cudaStream_t stream);
+/* embed_tokens for decode steps, DML:1725.  ids int64 [n] on device. */
+int dl_embed_rows(const int64_t* ids, const void* table, void* out, int n, int H, cudaStream_t stream);
+
+/* ---- CLIP front end: HF CLIPVisionEmbeddings (transformers, unvendored) + feature_select ---- */
+int dl_im2col_patches(const void* pixels, void* out, int B, int C, int S, int ps, int Kpad, cudaStream_t stream);
+int dl_clip_assemble(const void* patch_embed, const void* cls, const void* pos, void* out, int B, int NP, int C,
+                     cudaStream_t stream);
+/* multimodal_encoder/clip_encoder.py:43-51 (select_feature == "patch") */
+int dl_drop_cls(const void* x, void* out, int B, int NP, int C, cudaStream_t stream);
+
+/* ---- K1: predictor score + top-k + gather/compact + index map + CSR header, DML:1867, :1897-1994 ------------- */
+/* logits [B,n_img,2]; forced_keep int64 [B,k] or NULL; hidden_in [B,P,H]; hidden_out [B,P',H], P' = P-n_img+k;
+ * keep_index int64 [B,k] ascending; pos_out int32 [B,P'] original positions; cu_seqlens int32 [B+1].
+ * ctas_per_sample <= 0 picks a grid that fills 148 SMs. */
+int dl_select_compact(const void* logits, const int64_t* forced_keep, const void* hidden_in, void* hidden_out,
+                      int64_t* keep_index, int32_t* pos_out, int32_t* cu_seqlens, int B, int P, int H, int img_start,
+                      int n_img, int k, int ctas_per_sample, cudaStream_t stream);
+
+/* ---- K4+K5: RoPE + (conditional) KV append, DML:253-285, :1043-1083; CU:109-268 ------------------------------- */
+/* qkv [n_tok, 3H] = [q|k|v], q rotated in place; pos int32 [n_tok]; cu_seqlens int32 [B+1]; kv_len int32 [B] = slot
+ * base of this layer; keep uint8 [n_tok] or NULL; cos/sin [max_pos, hd]; arenas [B, heads, cap, hd];
+ * k_side/v_side [n_tok, heads, hd] or NULL. */
+int dl_rope_append(void* qkv, const int32_t* pos, const int32_t* cu_seqlens, const int32_t* kv_len, const uint8_t* keep,
+                   const void* cos_table, const void* sin_table, void* k_arena, void* v_arena, void* k_side, void* v_side,
+                   int n_tok, int B, int heads, int head_dim, int cap, cudaStream_t stream);
+/* same, reading the skinny GEMM's split-K slices partial[splits][B][3H] (decode step, one token per sample). */
+int dl_dec_reduce_rope_append(const float* partial, int splits, void* q_out, const int32_t* pos, const int32_t* kv_len,
+                              const uint8_t* keep, const void* cos_table, const void* sin_table, void* k_arena,
+                              void* v_arena, void* k_side, void* v_side, int B, int heads, int head_dim, int cap,
+                              cudaStream_t stream);
+/* DynamicCachePlus.true_cache_length bookkeeping (CU:146-148, :162, :197-199, :250), on the device.
+ * kv_len int32 [L,B]; layers < sparse_layer += n_lo; layers >= sparse_layer += n_hi where keep (NULL = all);
+ * pos[b] += n_lo; step_counter[0] += 1 (either may be NULL). */
+int dl_kv_advance(int32_t* kv_len, int32_t* pos, int32_t* step_counter, const uint8_t* keep, int L, int B, int sparse_layer,
+                  int n_lo, int n_hi, cudaStream_t stream);
+
+/* ---- K7: VisionPredictor helpers, DML:1348-1359 (+ the re-stacking at :1832-1862 made unnecessary) ------------- */
+/* LayerNorm of rows x[b*x_batch_stride + i*H], i < rows_per_batch, into contiguous y [B*rows_per_batch, H]. */
+int dl_layernorm_strided(const void* x, const void* w, const void* b, void* y, int B, int rows_per_batch,
+                         int64_t x_batch_stride, int H, float eps, cudaStream_t stream);
+/* z = cat[y[..., :C/2], token-mean(y[..., C/2:]) broadcast]; g_scratch bf16 [B, C/2]. */
+int dl_predictor_mix(const void* y, void* g_scratch, void* z, int B, int N, int C, cudaStream_t stream);
+
+/* ---- K3: ragged split-KV decode attention, DML:1061-1122 with q_len == 1 -------------------------------------- */
+int64_t dl_attn_decode_workspace_bytes(int B, int heads, int n_split);
+/* q [B, heads*hd] (row stride q_row_stride elems); k_side/v_side [B, heads, hd] = the new token (NULL: cache only);
+ * kv_len int32 [B] cached keys (excl. the new token); out [B, heads*hd]; quirk_pad != 0 reproduces the reference's
+ * unmasked zero padding for B > 1 (CU:165-241). */
+int dl_attn_decode(const void* q, int q_row_stride, const void* k_arena, const void* v_arena, const void* k_side,
+                   const void* v_side, const int32_t* kv_len, void* out, void* workspace, int B, int heads, int head_dim,
+                   int cap, int n_split, float scale, int quirk_pad, cudaStream_t stream);
+
+/* ---- K2/K6/K7: variable-length attention (warp-MMA tile path), DML:1114-1122; CTL:164-169; HF CLIPAttention ---- */
+/* Addresses: Q(b,i,h) = q + (cu_q[b]+i)*q_tok_stride + h*q_head_stride;
+ * K(b,j,h) = k + b*kv_batch_stride + h*kv_head_stride + ((kv_packed ? cu_q[b] : 0) + j)*kv_tok_stride (V alike);
+ * O(b,i,h) = out + (cu_q[b]+i)*o_tok_stride + h*head_dim.  kv_past int32 [B] or NULL: keys already cached before this
+ * pass (query i attends keys j <= i + kv_past[b] when causal). head_dim 64 or 128. */
+int dl_attn_varlen(const void* q, int64_t q_tok_stride, int64_t q_head_stride, const void* k, const void* v,
+                   int64_t kv_batch_stride, int64_t kv_head_stride, int64_t kv_tok_stride, int kv_packed, void* out,
+                   int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int B, int heads, int head_dim,
+                   int max_q_len, int causal, float scale, cudaStream_t stream);
+/* K2 proper: TMA + tcgen05/TMEM causal prefill attention, head_dim 128, K/V in the arena (attn_prefill_tc.cu). */
+int dl_attn_prefill_tc(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
+                       int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
+                       int cap, int max_q_len, float scale, cudaStream_t stream);
+
+/* ---- decode-step weight streaming: every nn.Linear at q_len == 1 (DML:1011-1013, :1127, :328, :2709) ----------- */
+/* partial fp32 [splits, M, N] = per-split X[M,K] . W[N,K]^T; M <= 64, K % 64 == 0.  TMA + tcgen05. */
+int dl_skinny_gemm_splits(int N, int K, int target_ctas);
+int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits, cudaStream_t stream);
+int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                    uint32_t box_rows, uint32_t box_cols);
+int dl_dec_reduce_bf16(const float* partial, void* y, int M, int N, int splits, cudaStream_t stream);
+int dl_dec_reduce_residual_norm(const float* partial, void* x, const void* norm_w, void* xn, int M, int H, int splits,
+                                float eps, cudaStream_t stream);
+int dl_dec_reduce_swiglu(const float* partial, void* act, int M, int I, int splits, cudaStream_t stream);
+/* TextPredictor tail + decode decision, DML:1374-1387, :2385-2391.  partial = split-K slices of Linear(H->D)(LN(x));
+ * forced uint8 [n_steps,B] or NULL overrides with forced[(step_counter[0]+forced_offset)*B + b]. */
+int dl_text_decision(const float* partial, int splits, int B, int D, const void* b1, const void* w3, const void* b3,
+                     const void* w5, const void* b5, const void* w7, const void* b7, const uint8_t* forced,
+                     const int32_t* step_counter, int forced_offset, uint8_t* keep, void* logits_out, cudaStream_t stream);
+
+/* ---- greedy next token: transformers-4.37.2 greedy search step ------------------------------ */
+/* logits bf16 [B,V]; next_ids int64 [B]; tokens_out int64 [B,out_stride] slot step_counter[0] (NULL: skip);
+ * finished int32 [B]; eos_token_id < 0 disables EOS tracking. */
+int dl_greedy_next(const void* logits, int B, int V, int64_t* next_ids, int64_t* tokens_out, int out_stride,
+                   const int32_t* step_counter, int32_t* finished, int eos_token_id, int pad_token_id, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNLLAVA_B200_H */

@@ -1,0 +1,127 @@
+"""Host-side logic that needs no GPU: state-dict key contract, ragged arena + legacy view semantics, sharding (gloo,
+world_size 2), synthetic input determinism."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+from dynamic_llava_b200.cache import LegacyPastView, RaggedKVArena
+from dynamic_llava_b200.presets import SPARSE_DEFAULTS, preset
+from dynamic_llava_b200.sharding import chunk_bounds, gather_token_ids, get_chunk, max_over_ranks
+from dynamic_llava_b200.synthetic import forced_text_decisions, numpy_state_dict, synthetic_inputs, weight_shapes
+
+
+def test_state_dict_keys_match_reference_contract():
+    cfg = DynamicLlavaConfig.from_preset("toy")
+    cfg.sparse_config["use_output_text_predictor"] = True
+    m = DynamicLlavaLlamaForCausalLM(cfg, device="cpu")
+    m.get_vision_tower().load_model()
+    keys = set(m.state_dict())
+    want = {k for k, _, _ in weight_shapes(cfg.to_dict())}
+    assert keys == want
+    for k in ("model.embed_tokens.weight", "model.layers.0.self_attn.q_proj.weight", "model.layers.3.mlp.down_proj.weight",
+              "model.norm.weight", "lm_head.weight", "model.mm_projector.0.bias", "model.mm_projector.2.weight",
+              "model.image_score_predictor.down_mlp.0.weight", "model.image_score_predictor.transformer.1.attn.qkv.weight",
+              "model.image_score_predictor.output_mlp.4.bias", "model.output_text_score_predictor.output_mlp.7.weight",
+              "model.vision_tower.vision_tower.vision_model.embeddings.class_embedding",
+              "model.vision_tower.vision_tower.vision_model.encoder.layers.0.self_attn.out_proj.bias",
+              "model.vision_tower.vision_tower.vision_model.pre_layrnorm.weight"):
+        assert k in keys, k
+    assert "model.image_score_predictor.transformer.0.attn.qkv.bias" not in keys  # qkv_bias=False
+    sd = numpy_state_dict(cfg.to_dict(), 0)
+    assert m.load_state_dict(sd, strict=True)
+
+
+def test_sparse_config_defaults_and_keep_counts():
+    assert SPARSE_DEFAULTS["sparse_layer"] == 2 and SPARSE_DEFAULTS["vision_keep_rate"] == 0.2
+    assert [int(576 * r) for r in (0.1, 0.2, 0.5, 1.0)] == [57, 115, 288, 576]
+    cfg = DynamicLlavaConfig.from_preset("llava-1.5-7b")
+    cfg.sparse_config["vision_keep_rate"] = 0.5  # live, mutable dict
+    assert cfg.sparse_config["vision_keep_rate"] == 0.5 and preset("llava-1.5-7b")["sparse_config"]["vision_keep_rate"] == 0.2
+
+
+def test_arena_legacy_view_is_zero_padded_ragged():
+    a = RaggedKVArena(n_layers=4, sparse_layer=2, batch=2, heads=2, head_dim=8, cap_lo=16, cap_hi=12, device="cpu", dtype=torch.float32)
+    # emulate: prefill 10 / 6 tokens, then one decode step kept by sample 1 only
+    for l in range(4):
+        k, v, cap = a.layer(l)
+        n = 10 if l < 2 else 6
+        k[:, :, :n] = 1.0
+        v[:, :, :n] = 2.0
+        a.kv_len[l] = n
+    a.host_len_lo, a.host_ub_hi = 10, 6
+    for l in range(4):
+        k, v, _ = a.layer(l)
+        if l < 2:
+            k[:, :, 10] = 3.0
+            a.kv_len[l] += 1
+        else:
+            k[1, :, 6] = 3.0
+            a.kv_len[l, 1] += 1
+    a.host_len_lo += 1
+    a.host_ub_hi += 1
+    a.hi_exact = False
+    past = LegacyPastView(a)
+    assert len(past) == 2 and len(past[0]) == 4
+    assert past[0][0][0].shape == (2, 2, 11, 8)            # dynamic_modeling_llama.py:2831 reads .shape[2]
+    assert past[0][-1][0].shape[-2] == 7                   # model_lvis_for_meteor.py:177
+    assert (past[0][-1][0][0, :, 6] == 0).all()            # shorter sample: zero pad, like cache_utils.py:204-235
+    assert (past[0][-1][0][1, :, 6] == 3).all()
+    tl = past[1]
+    assert [t.tolist() for t in tl] == [[11, 11], [11, 11], [6, 7], [6, 7]] and tl[0].dtype == torch.int64
+    a.grow(40, 30)
+    assert a.layer(0)[0].shape[2] == 40 and (a.layer(3)[0][1, :, 6] == 3).all() and a.room() == 23
+    a.reset()
+    assert int(a.kv_len.sum()) == 0 and float(a.k_hi.abs().sum()) == 0
+
+
+def test_chunk_rule_matches_reference_split_list():
+    import math
+    for n in (0, 1, 7, 8, 9, 64, 65):
+        for w in (1, 2, 4, 8):
+            size = math.ceil(n / w) if n else 0
+            ref = [list(range(n))[i:i + size] for i in range(0, n, size)] if n else []
+            for k in range(w):
+                want = ref[k] if k < len(ref) else []
+                assert get_chunk(list(range(n)), w, k) == want
+                lo, hi = chunk_bounds(n, w, k)
+                assert hi - lo == len(want)
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = chunk_bounds(n_items, world, rank)
+    local = torch.arange(lo, hi).reshape(-1, 1).repeat(1, 3) * 10 + torch.arange(3)
+    full = gather_token_ids(local, n_items)
+    t = max_over_ranks(1.0 + rank, "cpu")
+    if rank == 0:
+        q.put((full.tolist(), t))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [8, 7])
+def test_replica_sharding_gloo_world2(n_items):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + n_items
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    full, t = q.get(timeout=120)
+    for p in ps:
+        p.join(60)
+    want = (torch.arange(n_items).reshape(-1, 1).repeat(1, 3) * 10 + torch.arange(3)).tolist()
+    assert full == want and t == 2.0
+
+
+def test_synthetic_inputs_are_deterministic():
+    cfg = preset("toy")
+    a, pa = synthetic_inputs(cfg, 2, 12, seed=1)
+    b, pb = synthetic_inputs(cfg, 2, 12, seed=1)
+    assert torch.equal(a, b) and torch.equal(pa, pb) and (a[:, 5] == -200).all() and (a[:, 0] == 1).all()
+    d = forced_text_decisions(11, 2, keep_rate=[0.3, 0.7], seed=3)
+    assert d.shape == (11, 2) and d.dtype == torch.bool
