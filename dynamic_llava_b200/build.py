@@ -53,6 +53,8 @@ def _stale(out: str, deps) -> bool:
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "dynllava_b200.h")]
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if not force and not _stale(LIB, srcs + hdrs):
+        return LIB  # up to date (the GPU box receives the prebuilt .so with the snapshot)
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
