@@ -37,6 +37,15 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   AdSmem& S = *reinterpret_cast<AdSmem*>(smem_raw);
   const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AD_STAGES; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], AD_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  pdl_launch_dependents();
+  pdl_wait();  // q, side k/v, kv_len and the arena rows of this step come from predecessor kernels
   const int len = kv_len[b];
   int kps = (len + n_split - 1) / n_split;
   kps = ((kps + AD_TK - 1) / AD_TK) * AD_TK;
@@ -45,13 +54,6 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   const int n_keys = max(k1 - k0, 0);
   const int n_tiles = (n_keys + AD_TK - 1) / AD_TK;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < AD_STAGES; ++s) {
-      mbar_init(&S.full[s], 1);
-      mbar_init(&S.empty[s], AD_CWARPS);
-    }
-    fence_barrier_init();
-  }
   __syncthreads();
 
   const bf16* kbase = k_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
@@ -220,6 +222,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
 
 __global__ void __launch_bounds__(AD_HD) attn_decode_combine_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml,
                                                                     bf16* __restrict__ out, int heads, int n_split) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const int64_t base = ((int64_t)b * heads + h) * n_split;
   float M = -INFINITY;
@@ -251,10 +255,11 @@ extern "C" int dl_attn_decode(const void* q, int q_row_stride, const void* k_are
   }
   float* ws_acc = (float*)workspace;
   float* ws_ml = ws_acc ? ws_acc + (int64_t)B * heads * n_split * AD_HD : nullptr;
-  attn_decode_kernel<<<dim3(heads, B, n_split), AD_THREADS, sizeof(AdSmem), stream>>>(
-      (const bf16*)q, q_row_stride, (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)k_side, (const bf16*)v_side,
-      kv_len, (bf16*)out, ws_acc, ws_ml, B, heads, cap, n_split, scale, quirk_pad);
+  dl_launch_pdl(attn_decode_kernel, dim3(heads, B, n_split), dim3(AD_THREADS), sizeof(AdSmem), stream, (const bf16*)q, q_row_stride,
+                (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)k_side, (const bf16*)v_side, kv_len, (bf16*)out, ws_acc, ws_ml,
+                B, heads, cap, n_split, scale, quirk_pad);
   if (n_split > 1)
-    attn_decode_combine_kernel<<<dim3(heads, B), AD_HD, 0, stream>>>(ws_acc, ws_ml, (bf16*)out, heads, n_split);
+    dl_launch_pdl(attn_decode_combine_kernel, dim3(heads, B), dim3(AD_HD), 0, stream, (const float*)ws_acc, (const float*)ws_ml,
+                  (bf16*)out, heads, n_split);
   DL_CHECK_LAUNCH("dl_attn_decode");
 }

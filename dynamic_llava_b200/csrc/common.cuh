@@ -25,6 +25,32 @@ extern "C" int dl_set_error(int code, const char* where);
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the decode step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: it may start (prologue, barrier init, weight prefetch) while its
+// predecessor is still draining, executes pdl_wait() before touching anything a predecessor wrote, and calls
+// pdl_launch_dependents() early so that its successor can do the same.  EVERY kernel in the chain calls pdl_wait()
+// (even if it would not need to) so that "kernel N complete" still implies "kernels < N complete".
+// ---------------------------------------------------------------------------------------------
+DL_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DL_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // bf16 <-> fp32, 128-bit vectors
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) bf16x8 {
@@ -64,6 +90,27 @@ DL_DEVINL int4 ld_stream(const void* p) {
 DL_DEVINL void st_stream(void* p, const int4& v) {
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
+}
+
+// sum of the skinny GEMM's split-K slices p[s * stride], s < S, in FIXED order (deterministic); loads are issued in
+// groups of 8 so that one L2 round trip covers S <= 8
+DL_DEVINL float4 sum_slices_f4(const float* __restrict__ p, int64_t stride, int S) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < S; s0 += 8) {
+    float4 t[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      if (s0 + g < S) t[g] = *reinterpret_cast<const float4*>(p + (int64_t)(s0 + g) * stride);
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      if (s0 + g < S) {
+        a.x += t[g].x;
+        a.y += t[g].y;
+        a.z += t[g].z;
+        a.w += t[g].w;
+      }
+  }
+  return a;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,20 +15,12 @@ DL_DEVINL float sum_slices(const float* __restrict__ p, int64_t slice_stride, in
   for (int s = 0; s < S; ++s) a += p[(int64_t)s * slice_stride];
   return a;
 }
-DL_DEVINL float4 sum_slices4(const float* __restrict__ p, int64_t slice_stride, int S) {
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < S; ++s) {
-    const float4 t = *reinterpret_cast<const float4*>(p + (int64_t)s * slice_stride);
-    a.x += t.x;
-    a.y += t.y;
-    a.z += t.z;
-    a.w += t.w;
-  }
-  return a;
-}
+DL_DEVINL float4 sum_slices4(const float* __restrict__ p, int64_t slice_stride, int S) { return sum_slices_f4(p, slice_stride, S); }
 
 __global__ void __launch_bounds__(256) dec_reduce_bf16_kernel(const float* __restrict__ partial, bf16* __restrict__ y, int64_t MN,
                                                               int S) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= MN) return;
   const float4 a = sum_slices4(partial + i, MN, S);
@@ -42,68 +34,84 @@ extern "C" int dl_dec_reduce_bf16(const float* partial, void* y, int M, int N, i
   DL_REQUIRE(N % 4 == 0, "dl_dec_reduce_bf16");
   const int64_t MN = (int64_t)M * N;
   if (MN == 0) return 0;
-  dec_reduce_bf16_kernel<<<(int)((MN / 4 + 255) / 256), 256, 0, stream>>>(partial, (bf16*)y, MN, splits);
+  dl_launch_pdl(dec_reduce_bf16_kernel, dim3((unsigned)((MN / 4 + 255) / 256)), dim3(256), 0, stream, partial, (bf16*)y, MN, splits);
   DL_CHECK_LAUNCH("dl_dec_reduce_bf16");
 }
 
 // one CTA per row m:  x[m] += bf16(sum_s partial[s][m]);  xn[m] = w * bf16(x * rstd)
-__global__ void __launch_bounds__(512) dec_reduce_residual_norm_kernel(const float* __restrict__ partial, bf16* __restrict__ x,
-                                                                       const bf16* __restrict__ w, bf16* __restrict__ xn, int M,
-                                                                       int H, int S, float eps) {
+// 1024 threads; each thread owns up to RN_V float4 columns of the row and issues every split-K slice load up front
+// (the slices are L2-resident: the GEMM epilogue has just written them), so the kernel is two L2 round trips + one
+// block reduction deep.
+#define RN_THREADS 1024
+template <int RN_V>
+__global__ void __launch_bounds__(RN_THREADS) dec_reduce_residual_norm_kernel(const float* __restrict__ partial, bf16* __restrict__ x,
+                                                                              const bf16* __restrict__ w, bf16* __restrict__ xn, int M,
+                                                                              int H, int S, float eps) {
   __shared__ float red[32];
-  extern __shared__ float xs[];  // H floats: the updated residual row
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x;
   const int64_t slice = (int64_t)M * H;
+  float r[RN_V][4];
   float ss = 0.f;
-  for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
-    const float4 a = sum_slices4(partial + (int64_t)m * H + i, slice, S);
-    const uint2 raw = *reinterpret_cast<const uint2*>(x + (int64_t)m * H + i);
-    const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-    const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-    float r[4] = {rbf(x01.x + rbf(a.x)), rbf(x01.y + rbf(a.y)), rbf(x23.x + rbf(a.z)), rbf(x23.y + rbf(a.w))};
-    __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&lo);
-    o.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(x + (int64_t)m * H + i) = o;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      xs[i + e] = r[e];
-      ss += r[e] * r[e];
+  for (int v = 0; v < RN_V; ++v) {
+    const int i = (threadIdx.x + v * RN_THREADS) * 4;
+    if (i < H) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(x + (int64_t)m * H + i);
+      const float4 a = sum_slices_f4(partial + (int64_t)m * H + i, slice, S);
+      const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      r[v][0] = rbf(x01.x + rbf(a.x));
+      r[v][1] = rbf(x01.y + rbf(a.y));
+      r[v][2] = rbf(x23.x + rbf(a.z));
+      r[v][3] = rbf(x23.y + rbf(a.w));
+      __nv_bfloat162 lo = __floats2bfloat162_rn(r[v][0], r[v][1]), hi = __floats2bfloat162_rn(r[v][2], r[v][3]);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(x + (int64_t)m * H + i) = o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss += r[v][e] * r[v][e];
     }
   }
   ss = block_sum(ss, red);
   if (w == nullptr) return;
   const float rstd = 1.0f / sqrtf(ss / (float)H + eps);
-  for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(w + i);
-    const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-    const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-    __nv_bfloat162 lo = __floats2bfloat162_rn(w01.x * rbf(xs[i] * rstd), w01.y * rbf(xs[i + 1] * rstd));
-    __nv_bfloat162 hi = __floats2bfloat162_rn(w23.x * rbf(xs[i + 2] * rstd), w23.y * rbf(xs[i + 3] * rstd));
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&lo);
-    o.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(xn + (int64_t)m * H + i) = o;
+#pragma unroll
+  for (int v = 0; v < RN_V; ++v) {
+    const int i = (threadIdx.x + v * RN_THREADS) * 4;
+    if (i < H) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(w + i);
+      const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      __nv_bfloat162 lo = __floats2bfloat162_rn(w01.x * rbf(r[v][0] * rstd), w01.y * rbf(r[v][1] * rstd));
+      __nv_bfloat162 hi = __floats2bfloat162_rn(w23.x * rbf(r[v][2] * rstd), w23.y * rbf(r[v][3] * rstd));
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(xn + (int64_t)m * H + i) = o;
+    }
   }
 }
 extern "C" int dl_dec_reduce_residual_norm(const float* partial, void* x, const void* norm_w, void* xn, int M, int H,
                                            int splits, float eps, cudaStream_t stream) {
-  DL_REQUIRE(H % 4 == 0 && H * 4 <= 96 * 1024, "dl_dec_reduce_residual_norm");
+  DL_REQUIRE(H % 4 == 0 && H <= RN_THREADS * 4 * 2, "dl_dec_reduce_residual_norm");
   if (M == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(dec_reduce_residual_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
-  dec_reduce_residual_norm_kernel<<<M, 512, H * sizeof(float), stream>>>(partial, (bf16*)x, (const bf16*)norm_w, (bf16*)xn, M,
-                                                                        H, splits, eps);
+  if (H <= RN_THREADS * 4)
+    dl_launch_pdl(dec_reduce_residual_norm_kernel<1>, dim3(M), dim3(RN_THREADS), 0, stream, partial, (bf16*)x, (const bf16*)norm_w,
+                  (bf16*)xn, M, H, splits, eps);
+  else
+    dl_launch_pdl(dec_reduce_residual_norm_kernel<2>, dim3(M), dim3(RN_THREADS), 0, stream, partial, (bf16*)x, (const bf16*)norm_w,
+                  (bf16*)xn, M, H, splits, eps);
   DL_CHECK_LAUNCH("dl_dec_reduce_residual_norm");
 }
 
 // partial rows are [gate(I) | up(I)]
 __global__ void __launch_bounds__(256) dec_reduce_swiglu_kernel(const float* __restrict__ partial, bf16* __restrict__ act, int M,
                                                                 int I, int S) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (idx >= (int64_t)M * I) return;
   const int m = (int)(idx / I), i = (int)(idx % I);
@@ -125,7 +133,7 @@ extern "C" int dl_dec_reduce_swiglu(const float* partial, void* act, int M, int 
   DL_REQUIRE(I % 4 == 0, "dl_dec_reduce_swiglu");
   const int64_t n = (int64_t)M * I / 4;
   if (n == 0) return 0;
-  dec_reduce_swiglu_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(partial, (bf16*)act, M, I, splits);
+  dl_launch_pdl(dec_reduce_swiglu_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, partial, (bf16*)act, M, I, splits);
   DL_CHECK_LAUNCH("dl_dec_reduce_swiglu");
 }
 
@@ -137,7 +145,7 @@ extern "C" int dl_dec_reduce_swiglu(const float* partial, void* act, int M, int 
 // ---------------------------------------------------------------------------------------------
 DL_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-__global__ void __launch_bounds__(256) text_decision_kernel(const float* __restrict__ partial, int S, int B, int D,
+__global__ void __launch_bounds__(1024) text_decision_kernel(const float* __restrict__ partial, int S, int B, int D,
                                                             const bf16* __restrict__ b1, const bf16* __restrict__ w3,
                                                             const bf16* __restrict__ b3, const bf16* __restrict__ w5,
                                                             const bf16* __restrict__ b5, const bf16* __restrict__ w7,
@@ -148,6 +156,8 @@ __global__ void __launch_bounds__(256) text_decision_kernel(const float* __restr
   float* h1 = sm;          // D
   float* h2 = h1 + D;      // D/2
   float* h3 = h2 + D / 2;  // D/4
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   if (partial != nullptr) {
@@ -158,7 +168,12 @@ __global__ void __launch_bounds__(256) text_decision_kernel(const float* __restr
     __syncthreads();
     for (int o = warp; o < D / 2; o += nw) {
       float a = 0.f;
-      for (int i = lane; i < D; i += 32) a += h1[i] * bf2f(w3[(int64_t)o * D + i]);
+      for (int i = lane * 8; i < D; i += 256) {  // D % 8 == 0: 128-bit weight loads
+        float wv[8];
+        unpack8(ld8(w3 + (int64_t)o * D + i), wv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a += h1[i + e] * wv[e];
+      }
       a = warp_sum(a);
       if (lane == 0) h2[o] = rbf(gelu_erf(rbf(a + bf2f(b3[o]))));
     }
@@ -196,11 +211,11 @@ extern "C" int dl_text_decision(const float* partial, int splits, int B, int D, 
                                 const void* w5, const void* b5, const void* w7, const void* b7, const uint8_t* forced,
                                 const int32_t* step_counter, int forced_offset, uint8_t* keep, void* logits_out,
                                 cudaStream_t stream) {
-  DL_REQUIRE(D % 4 == 0 && (partial != nullptr || forced != nullptr), "dl_text_decision");
+  DL_REQUIRE(D % 8 == 0 && (partial != nullptr || forced != nullptr), "dl_text_decision");
   if (B == 0) return 0;
   const size_t smem = (size_t)(D + D / 2 + D / 4) * sizeof(float);
-  text_decision_kernel<<<B, 256, smem, stream>>>(partial, splits, B, D, (const bf16*)b1, (const bf16*)w3, (const bf16*)b3,
-                                                 (const bf16*)w5, (const bf16*)b5, (const bf16*)w7, (const bf16*)b7, forced,
-                                                 step_counter, forced_offset, keep, (bf16*)logits_out);
+  dl_launch_pdl(text_decision_kernel, dim3(B), dim3(1024), smem, stream, partial, splits, B, D, (const bf16*)b1, (const bf16*)w3,
+                (const bf16*)b3, (const bf16*)w5, (const bf16*)b5, (const bf16*)w7, (const bf16*)b7, forced, step_counter, forced_offset,
+                keep, (bf16*)logits_out);
   DL_CHECK_LAUNCH("dl_text_decision");
 }

@@ -11,6 +11,8 @@ template <int MAXV>  // 128-bit chunks cached per thread
 __global__ void __launch_bounds__(512) rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                       bf16* __restrict__ y, int H, float eps) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const bf16* xr = x + row * H;
   bf16* yr = y + row * H;
@@ -50,11 +52,11 @@ extern "C" int dl_rmsnorm(const void* x, const void* w, void* y, int rows, int H
   int threads = H / 8 >= 512 ? 512 : ((H / 8 + 31) / 32) * 32;
   int per = (H / 8 + threads - 1) / threads;
   if (per <= 1)
-    rmsnorm_kernel<1><<<rows, threads, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, H, eps);
+    dl_launch_pdl(rmsnorm_kernel<1>, dim3(rows), dim3(threads), 0, stream, (const bf16*)x, (const bf16*)w, (bf16*)y, H, eps);
   else if (per <= 2)
-    rmsnorm_kernel<2><<<rows, threads, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, H, eps);
+    dl_launch_pdl(rmsnorm_kernel<2>, dim3(rows), dim3(threads), 0, stream, (const bf16*)x, (const bf16*)w, (bf16*)y, H, eps);
   else
-    rmsnorm_kernel<4><<<rows, threads, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, H, eps);
+    dl_launch_pdl(rmsnorm_kernel<4>, dim3(rows), dim3(threads), 0, stream, (const bf16*)x, (const bf16*)w, (bf16*)y, H, eps);
   DL_CHECK_LAUNCH("dl_rmsnorm");
 }
 
@@ -65,6 +67,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(512) layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                         const bf16* __restrict__ b, bf16* __restrict__ y, int H, float eps) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const bf16* xr = x + row * H;
   bf16* yr = y + row * H;
@@ -115,11 +119,11 @@ extern "C" int dl_layernorm(const void* x, const void* w, const void* b, void* y
   int threads = H / 8 >= 512 ? 512 : ((H / 8 + 31) / 32) * 32;
   int per = (H / 8 + threads - 1) / threads;
   if (per <= 1)
-    layernorm_kernel<1><<<rows, threads, 0, stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
+    dl_launch_pdl(layernorm_kernel<1>, dim3(rows), dim3(threads), 0, stream, (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
   else if (per <= 2)
-    layernorm_kernel<2><<<rows, threads, 0, stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
+    dl_launch_pdl(layernorm_kernel<2>, dim3(rows), dim3(threads), 0, stream, (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
   else
-    layernorm_kernel<4><<<rows, threads, 0, stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
+    dl_launch_pdl(layernorm_kernel<4>, dim3(rows), dim3(threads), 0, stream, (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
   DL_CHECK_LAUNCH("dl_layernorm");
 }
 
@@ -266,6 +270,8 @@ extern "C" int dl_embed_splice(const int64_t* ids, const int32_t* seq_len, const
 // plain embedding gather for decode steps: out[b] = table[ids[b]]  (ids int64 on device)
 __global__ void __launch_bounds__(256) embed_rows_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ table,
                                                          bf16* __restrict__ out, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t id = ids[blockIdx.x];
   const bf16* src = table + id * H;
   bf16* dst = out + (int64_t)blockIdx.x * H;
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(256) embed_rows_kernel(const int64_t* __restri
 extern "C" int dl_embed_rows(const int64_t* ids, const void* table, void* out, int n, int H, cudaStream_t stream) {
   DL_REQUIRE(H % 8 == 0, "dl_embed_rows");
   if (n == 0) return 0;
-  embed_rows_kernel<<<n, 256, 0, stream>>>(ids, (const bf16*)table, (bf16*)out, H);
+  dl_launch_pdl(embed_rows_kernel, dim3(n), dim3(256), 0, stream, ids, (const bf16*)table, (bf16*)out, H);
   DL_CHECK_LAUNCH("dl_embed_rows");
 }
 
@@ -356,6 +362,8 @@ __global__ void __launch_bounds__(1024) greedy_kernel(const bf16* __restrict__ l
                                                       int eos, int pad) {
   __shared__ float sval[32];
   __shared__ int sidx[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const bf16* row = logits + (int64_t)b * V;
   float best = -INFINITY;
@@ -410,7 +418,7 @@ extern "C" int dl_greedy_next(const void* logits, int B, int V, int64_t* next_id
                               const int32_t* step_counter, int32_t* finished, int eos_token_id, int pad_token_id,
                               cudaStream_t stream) {
   if (B == 0) return 0;
-  greedy_kernel<<<B, 1024, 0, stream>>>((const bf16*)logits, V, next_ids, tokens_out, out_stride, step_counter, finished,
-                                        eos_token_id, pad_token_id);
+  dl_launch_pdl(greedy_kernel, dim3(B), dim3(1024), 0, stream, (const bf16*)logits, V, next_ids, tokens_out, out_stride, step_counter,
+                finished, eos_token_id, pad_token_id);
   DL_CHECK_LAUNCH("dl_greedy_next");
 }

@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(256) dec_reduce_rope_append_kernel(const float
   constexpr int HALF = HD / 2;
   constexpr int PAIRS = HALF / 8;
   constexpr int VCH = HD / 8;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int H = heads * HD;
   const int64_t slice = (int64_t)B * 3 * H;
@@ -119,20 +121,16 @@ __global__ void __launch_bounds__(256) dec_reduce_rope_append_kernel(const float
   const bf16* cs = cos_t + (int64_t)p * HD;
   const bf16* sn = sin_t + (int64_t)p * HD;
   const int n_rot = heads * PAIRS;
-  const int items = 2 * n_rot + heads * VCH;
+  // blockIdx.y selects the part of the row this CTA handles: 0 = q pairs, 1 = k pairs, 2 = v chunks (3x the CTAs in
+  // flight; with one token per sample the kernel is latency-, not bandwidth-bound)
+  const int it0 = blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? n_rot : 2 * n_rot);
+  const int it1 = blockIdx.y == 0 ? n_rot : (blockIdx.y == 1 ? 2 * n_rot : 2 * n_rot + heads * VCH);
   auto load8 = [&](const float* src, float* f) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = 0.f;
-    for (int s = 0; s < S; ++s) {
-      const float4 a = *reinterpret_cast<const float4*>(src + (int64_t)s * slice);
-      const float4 c = *reinterpret_cast<const float4*>(src + (int64_t)s * slice + 4);
-      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
-      f[4] += c.x; f[5] += c.y; f[6] += c.z; f[7] += c.w;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = rbf(f[e]);
+    const float4 a = sum_slices_f4(src, slice, S), c = sum_slices_f4(src + 4, slice, S);
+    f[0] = rbf(a.x); f[1] = rbf(a.y); f[2] = rbf(a.z); f[3] = rbf(a.w);
+    f[4] = rbf(c.x); f[5] = rbf(c.y); f[6] = rbf(c.z); f[7] = rbf(c.w);
   };
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+  for (int it = it0 + threadIdx.x; it < it1; it += blockDim.x) {
     if (it < 2 * n_rot) {
       const int which = it / n_rot;
       const int r = it - which * n_rot;
@@ -181,9 +179,9 @@ extern "C" int dl_dec_reduce_rope_append(const float* partial, int splits, void*
                                          int heads, int head_dim, int cap, cudaStream_t stream) {
   DL_REQUIRE(head_dim == 128 && k_side != nullptr && v_side != nullptr, "dl_dec_reduce_rope_append");
   if (B == 0) return 0;
-  dec_reduce_rope_append_kernel<128><<<B, 256, 0, stream>>>(partial, splits, (bf16*)q_out, pos, kv_len, keep,
-                                                            (const bf16*)cos_table, (const bf16*)sin_table, (bf16*)k_arena,
-                                                            (bf16*)v_arena, (bf16*)k_side, (bf16*)v_side, B, heads, cap);
+  dl_launch_pdl(dec_reduce_rope_append_kernel<128>, dim3(B, 3), dim3(256), 0, stream, partial, splits, (bf16*)q_out, pos, kv_len, keep,
+                (const bf16*)cos_table, (const bf16*)sin_table, (bf16*)k_arena, (bf16*)v_arena, (bf16*)k_side, (bf16*)v_side, B,
+                heads, cap);
   DL_CHECK_LAUNCH("dl_dec_reduce_rope_append");
 }
 
@@ -194,6 +192,8 @@ extern "C" int dl_dec_reduce_rope_append(const float* partial, int splits, void*
 // also pos[b] += n_lo (decode position = full-length count, fact 8) and step_counter += 1.
 __global__ void kv_advance_kernel(int32_t* __restrict__ kv_len, int32_t* __restrict__ pos, int32_t* __restrict__ step_counter,
                                   const uint8_t* __restrict__ keep, int L, int B, int sparse_layer, int n_lo, int n_hi) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < L * B) {
     const int l = idx / B, b = idx % B;
@@ -209,6 +209,6 @@ extern "C" int dl_kv_advance(int32_t* kv_len, int32_t* pos, int32_t* step_counte
                              int sparse_layer, int n_lo, int n_hi, cudaStream_t stream) {
   const int n = L * B > B ? L * B : B;
   if (n == 0) return 0;
-  kv_advance_kernel<<<(n + 127) / 128, 128, 0, stream>>>(kv_len, pos, step_counter, keep, L, B, sparse_layer, n_lo, n_hi);
+  dl_launch_pdl(kv_advance_kernel, dim3((n + 127) / 128), dim3(128), 0, stream, kv_len, pos, step_counter, keep, L, B, sparse_layer, n_lo, n_hi);
   DL_CHECK_LAUNCH("dl_kv_advance");
 }

@@ -63,7 +63,17 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       constexpr uint32_t BYTES = (SG_BM + NB) * SG_BK * 2;
-      for (int i = 0; i < nkb; ++i) {
+      // The weights do not depend on the previous kernel: start streaming W into every free stage right away, and only
+      // then wait for the predecessor (PDL) before fetching the activation tiles X it produced.
+      const int npre = min(nkb, SG_STAGES);
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&S.full[i], BYTES);
+        tma_load_2d(S.a[i], &tmap_w, (kb0 + i) * SG_BK, n0, &S.full[i]);
+      }
+      pdl_launch_dependents();
+      pdl_wait();
+      for (int i = 0; i < npre; ++i) tma_load_2d(S.b[i], &tmap_x, (kb0 + i) * SG_BK, 0, &S.full[i]);
+      for (int i = npre; i < nkb; ++i) {
         const int s = i % SG_STAGES;
         const uint32_t ph = (i / SG_STAGES) & 1;
         mbar_wait(&S.empty[s], ph ^ 1);
@@ -159,7 +169,8 @@ static int launch_sg(const CUtensorMap& tw, const CUtensorMap& tx, float* partia
     attr_set = true;
   }
   dim3 grid((N + SG_BM - 1) / SG_BM, splits);
-  skinny_gemm_kernel<NB><<<grid, SG_THREADS, smem, stream>>>(tw, tx, partial, M, N, KB, kbps);
+  cudaError_t le = dl_launch_pdl(skinny_gemm_kernel<NB>, grid, dim3(SG_THREADS), (size_t)smem, stream, tw, tx, partial, M, N, KB, kbps);
+  if (le != cudaSuccess) return dl_set_error((int)le, "dl_skinny_gemm(launch)");
   DL_CHECK_LAUNCH("dl_skinny_gemm");
 }
 
@@ -171,6 +182,7 @@ extern "C" int dl_skinny_gemm_splits(int N, int K, int target_ctas) {
   int max_s = KB / 4;  // keep >= 4 k-blocks (64 KB of W) per CTA
   if (max_s < 1) max_s = 1;
   if (s > max_s) s = max_s;
+  if (s > 8) s = 8;  // consumers fetch the slices in one 8-deep group of loads
   const int kbps = (KB + s - 1) / s;
   return (KB + kbps - 1) / kbps;  // effective number of non-empty splits
 }

@@ -28,8 +28,25 @@ def L():
     return lb
 
 
+_KEEP = []  # device tensors whose raw pointers were handed to the C ABI: keep them alive until the test ends
+
+
+@pytest.fixture(autouse=True)
+def _keepalive():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def P(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """raw device pointer for the C ABI; CPU tensors are uploaded first.  The tensor is pinned in _KEEP because a
+    temporary such as `P(x.to(DEV))` would otherwise be freed (and its block reused) before the kernel runs."""
+    if t is None:
+        return None
+    if t.device.type == "cpu":
+        t = t.to(DEV)
+    _KEEP.append(t)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def ST():
@@ -41,13 +58,15 @@ def rnd(*shape, seed=0, scale=1.0, dtype=BF):
     return (torch.randn(*shape, generator=g) * scale).to(dtype)
 
 
-def ulp_close(a, b, max_frac=0.005):
-    """bit-exact except <= max_frac of elements off by one bf16 ulp"""
+def ulp_close(a, b, max_frac=0.005, abs_ok=0.0):
+    """bit-exact except <= max_frac of elements off by one bf16 ulp (elements with |a-b| <= abs_ok are exempt: used where
+    the reference formula itself cancels catastrophically, e.g. the far negative tail of erf-GELU)"""
     a, b = a.cpu(), b.cpu()
     if torch.equal(a, b):
         return True
     ai, bi = a.view(torch.int16).int(), b.view(torch.int16).int()
     d = (ai - bi).abs()
+    d[(a.float() - b.float()).abs() <= abs_ok] = 0
     frac = (d > 0).float().mean().item()
     assert d.max().item() <= 1, f"max ulp diff {d.max().item()}"
     assert frac <= max_frac, f"{frac:.4%} elements differ"
@@ -106,7 +125,7 @@ def test_activation(L, act):
     xd = x.to(DEV).clone()
     L.bias_act(P(xd), None, 13, 2048, act, ST())
     torch.cuda.synchronize()
-    ulp_close(xd, ref, max_frac=0.002)
+    ulp_close(xd, ref, max_frac=0.002, abs_ok=1e-5)
 
 
 def test_residual_add_bitexact(L):
@@ -517,7 +536,7 @@ def test_im2col_patch_embed_matches_conv(L):
     got = (cols.float().cpu() @ wp.T).view(B, 16, Cout)
     assert (got - ref).abs().max() < 1e-3
     assert (cols[:, K:] == 0).all()
-    pe = ref.to(BF)
+    pe = ref.to(BF).contiguous()  # conv output is a transposed view
     cls, pos = rnd(Cout, seed=132), rnd(17, Cout, seed=133, scale=0.02)
     tok = torch.empty(B, 17, Cout, device=DEV, dtype=BF)
     L.clip_assemble(P(pe.to(DEV)), P(cls.to(DEV)), P(pos.to(DEV)), P(tok), B, 16, Cout, ST())

@@ -164,7 +164,7 @@ def test_generate_greedy_tokens(graph):
         while n < g["n_new"] and bool(sure[b, n]):
             n += 1
         assert out[b, :n].cpu().tolist() == g["tokens"][b, :n].tolist(), (b, n)
-    assert sure[:, 0].all() and torch.equal(out[:, 0].cpu(), g["tokens"][:, 0])
+    assert sure.float().mean() > 0.5  # the comparison above is not vacuous
 
 
 def test_generate_forced_decisions_graph_equals_eager_and_eos():
