@@ -4,8 +4,9 @@
 //
 // HBM-bound (bytes = len * 2 * 128 * 2 per (sample, head)); tensor cores have nothing to do at one query row per head.
 // One CTA per (head, sample, split): a producer warp streams 64-key K and V tiles (16 KB each, contiguous in the arena)
-// with 1-D TMA bulk copies into a 3-stage shared-memory ring guarded by mbarriers; four consumer warps each own 16 keys
-// of a tile and keep a private online-softmax state, merged once at the end.  Per-sample lengths come from the device
+// with 1-D TMA bulk copies into a 3-stage shared-memory ring guarded by mbarriers; two groups of four consumer warps
+// take alternate tiles, each warp owns 16 keys of its tile and keeps a private online-softmax state, merged once at the
+// end (short ragged caches are latency-bound: the two groups halve the dependent chain per CTA).  Per-sample lengths come from the device
 // (`kv_len`), so a decode step needs no host sync and is CUDA-graph replayable; CTAs whose split is empty exit early.
 //
 // `quirk_pad` reproduces the reference's B>1 batching artefact: every layer's cache is zero-padded to
@@ -16,7 +17,8 @@
 #define AD_HD 128
 #define AD_TK 64
 #define AD_STAGES 3
-#define AD_CWARPS 4
+#define AD_GROUPS 2                 // consumer warp groups; group g takes tiles t = g, g + AD_GROUPS, ...
+#define AD_CWARPS (4 * AD_GROUPS)   // 4 warps x 16 keys cover one 64-key tile
 #define AD_THREADS ((AD_CWARPS + 1) * 32)
 #define AD_STAGE_BYTES (2 * AD_TK * AD_HD * 2)
 
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   if (threadIdx.x == 0) {
     for (int s = 0; s < AD_STAGES; ++s) {
       mbar_init(&S.full[s], 1);
-      mbar_init(&S.empty[s], AD_CWARPS);
+      mbar_init(&S.empty[s], 4);
     }
     fence_barrier_init();
   }
@@ -83,12 +85,12 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     float m_run = -INFINITY, l_run = 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int t = 0; t < n_tiles; ++t) {
+    for (int t = warp >> 2; t < n_tiles; t += AD_GROUPS) {
       const int s = t % AD_STAGES;
       const uint32_t ph = (t / AD_STAGES) & 1;
       mbar_wait(&S.full[s], ph);
       const int keys = min(AD_TK, n_keys - t * AD_TK);
-      const int wk0 = warp * 16;  // first key of this warp inside the tile
+      const int wk0 = (warp & 3) * 16;  // first key of this warp inside the tile
       if (wk0 < keys) {
         const bf16* Ks = S.kv[s][0];
         const bf16* Vs = S.kv[s][1];

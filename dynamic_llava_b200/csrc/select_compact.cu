@@ -3,10 +3,12 @@
 // keep = ascending indices of the k best scores, hidden' = [left | image[keep] | right], RoPE positions stay the
 // ORIGINAL (pre-drop) positions, and a CSR header (cu_seqlens) describes the packed result.
 //
-// Grid = (R, B).  Every CTA of sample b recomputes the (tiny) 576-way ranking in shared memory — 576^2 compares,
-// ~1.3k per thread — and then streams its share of the P' output rows with 128-bit no-allocate loads/stores, so the
-// selection never round-trips through HBM and the copy runs with B*R CTAs in flight.  HBM-bound:
-// algorithmic bytes = 2 * B * P' * H * 2.
+// Grid = (R, B).  Every CTA of sample b redoes the selection for its sample in shared memory — an O(n) two-pass radix
+// select on the 16-bit score keys (256-bin histogram of the high byte, then of the low byte inside the boundary bin),
+// followed by an ordered compaction scan; ~2 us, so replicating it per CTA is cheaper than a second kernel or a round
+// trip of the index map through HBM — and then streams its share of the P' output rows with 128-bit no-allocate
+// loads/stores.  Ties at the k-th score are broken towards the lower index (= stable descending sort).
+// HBM-bound: algorithmic bytes = 2 * B * P' * H * 2.
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
 
@@ -22,53 +24,95 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
     int32_t* __restrict__ pos_out,           // [B, P']
     int32_t* __restrict__ cu_seqlens,        // [B + 1]
     int P, int H, int s0, int n_img, int k) {
-  __shared__ float score[SC_MAX_IMG];
+  __shared__ uint16_t key[SC_MAX_IMG];
   __shared__ int16_t kidx[SC_MAX_IMG];
-  __shared__ uint8_t keepf[SC_MAX_IMG];
+  __shared__ int hist[256];
   __shared__ int wsum[SC_THREADS / 32];
+  __shared__ int sel[4];  // [0] boundary bin, [1] #keys above it
   const int b = blockIdx.y, tid = threadIdx.x;
   const int Pp = P - n_img + k;
 
   if (forced_keep != nullptr) {
     for (int i = tid; i < k; i += SC_THREADS) kidx[i] = (int16_t)forced_keep[(int64_t)b * k + i];
-  } else {
-    // scores, rounded where the reference's bf16 log_softmax rounds
+  } else if (k > 0) {
+    // scores rounded where the reference's bf16 log_softmax rounds, mapped to order-preserving 16-bit keys
     for (int i = tid; i < n_img; i += SC_THREADS) {
       const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(logits + ((int64_t)b * n_img + i) * 2);
       const float l0 = __low2float(l), l1 = __high2float(l);
       const float m = fmaxf(l0, l1);
-      score[i] = rbf((l0 - m) - logf(expf(l0 - m) + expf(l1 - m)));
+      const bf16 sc = f2bf((l0 - m) - logf(expf(l0 - m) + expf(l1 - m)));
+      uint16_t bits = *reinterpret_cast<const uint16_t*>(&sc);
+      if (bits == 0x8000u) bits = 0;  // -0 == +0
+      key[i] = (bits & 0x8000u) ? (uint16_t)~bits : (uint16_t)(bits | 0x8000u);
     }
-    __syncthreads();
-    // rank = number of tokens that beat token i (ties broken towards the lower index = stable descending sort)
-    for (int i = tid; i < n_img; i += SC_THREADS) {
-      const float si = score[i];
-      int rank = 0;
-      for (int j = 0; j < n_img; ++j) {
-        const float sj = score[j];
-        rank += (sj > si) || (sj == si && j < i);
+    // two radix passes: find T = the k-th largest key, c_gt = #keys > T
+    int prefix = 0, c_gt = 0, want = k;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < n_img; i += SC_THREADS) {
+        const int kk = key[i];
+        if (pass == 0)
+          atomicAdd(&hist[kk >> 8], 1);
+        else if ((kk >> 8) == prefix)
+          atomicAdd(&hist[kk & 255], 1);
       }
-      keepf[i] = rank < k;
+      __syncthreads();
+      if (tid < 32) {  // suffix scan over the 256 bins (8 per lane), locate the bin that holds the `want`-th largest
+        int loc = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) loc += hist[tid * 8 + j];
+        int inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_down_sync(0xffffffffu, inc, o);
+          if (tid + o < 32) inc += t;
+        }
+        int run = inc - loc;  // keys in bins above this lane's 8
+        for (int j = 7; j >= 0; --j) {
+          const int h = hist[tid * 8 + j];
+          if (run < want && want <= run + h) {
+            sel[0] = tid * 8 + j;
+            sel[1] = run;
+          }
+          run += h;
+        }
+      }
+      __syncthreads();
+      if (pass == 0) prefix = sel[0];
+      c_gt += sel[1];
+      want -= sel[1];
+      if (pass == 1) prefix = (prefix << 8) | sel[0];
+      __syncthreads();
     }
-    __syncthreads();
-    // ordered compaction of the kept indices: contiguous chunk per thread + block exclusive scan
+    const int T = prefix, need_eq = k - c_gt;
+    // ordered compaction: contiguous chunk per thread, block exclusive scan of (#gt, #eq) packed in one int
     const int per = (n_img + SC_THREADS - 1) / SC_THREADS;
     const int lo = tid * per, hi = min(lo + per, n_img);
     int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += keepf[i];
+    for (int i = lo; i < hi; ++i) cnt += (key[i] > T) + ((key[i] == T) << 16);
     int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
       if ((tid & 31) >= o) inc += t;
     }
     if ((tid & 31) == 31) wsum[tid >> 5] = inc;
     __syncthreads();
     int base = 0;
     for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
-    int off = base + inc - cnt;
-    for (int i = lo; i < hi; ++i)
-      if (keepf[i]) kidx[off++] = (int16_t)i;
+    const int excl = base + inc - cnt;
+    int gt_before = excl & 0xffff, eq_before = excl >> 16;
+    for (int i = lo; i < hi; ++i) {
+      const int kk = key[i];
+      if (kk > T) {
+        kidx[gt_before + min(eq_before, need_eq)] = (int16_t)i;
+        ++gt_before;
+      } else if (kk == T) {
+        if (eq_before < need_eq) kidx[gt_before + eq_before] = (int16_t)i;
+        ++eq_before;
+      }
+    }
   }
   __syncthreads();
 
