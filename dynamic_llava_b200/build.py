@@ -24,6 +24,7 @@ SOURCES = [
     "attn_decode.cu",
     "attn_prefill_mma.cu",
     "attn_prefill_tc.cu",
+    "attn_prefill_tc2.cu",
     "skinny_gemm.cu",
     "decode_fused.cu",
     "predictor_ops.cu",

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   if (threadIdx.x == 0) {
     for (int s = 0; s < AD_STAGES; ++s) {
       mbar_init(&S.full[s], 1);
-      mbar_init(&S.empty[s], 4);
+      mbar_init(&S.empty[s], AD_CWARPS);
     }
     fence_barrier_init();
   }
@@ -85,13 +85,15 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     float m_run = -INFINITY, l_run = 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int t = warp >> 2; t < n_tiles; t += AD_GROUPS) {
+    // Every consumer warp observes EVERY phase of every stage barrier (parity waits alias if a waiter skips a phase);
+    // only the owning group (t mod AD_GROUPS) does the math, the other group releases the stage at once.
+    for (int t = 0; t < n_tiles; ++t) {
       const int s = t % AD_STAGES;
       const uint32_t ph = (t / AD_STAGES) & 1;
       mbar_wait(&S.full[s], ph);
       const int keys = min(AD_TK, n_keys - t * AD_TK);
       const int wk0 = (warp & 3) * 16;  // first key of this warp inside the tile
-      if (wk0 < keys) {
+      if ((t % AD_GROUPS) == (warp >> 2) && wk0 < keys) {
         const bf16* Ks = S.kv[s][0];
         const bf16* Vs = S.kv[s][1];
         float sc[8];

@@ -87,7 +87,7 @@ class Engine:
         if self.dtype != torch.bfloat16:
             raise RuntimeError("kernels compute in bf16: load the model with torch_dtype=torch.bfloat16")
         self.packed = None
-        self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc")  # "tc" (tcgen05) | "mma" (warp-MMA tile path)
+        self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc")  # "tc2" | "tc" (tcgen05 kernels) | "mma" (warp-MMA tile path)
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.launches = 0  # kernels of OURS launched (eager path; graph replays counted via launches_per_step)
         self.launches_per_step = 0
@@ -365,7 +365,9 @@ class Engine:
                            None, None, N, B, nh, hd, cap, _stream())
         attn = torch.empty(N, H, device=x.device, dtype=x.dtype)
         scale = 1.0 / math.sqrt(hd)
-        if self.prefill_attn == "tc":
+        if self.prefill_attn == "tc2":
+            self.L.attn_prefill_tc2(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())
+        elif self.prefill_attn == "tc":
             self.L.attn_prefill_tc(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())
         else:
             self.L.attn_varlen(_p(qkv), 3 * H, hd, _p(K), _p(V), nh * cap * hd, cap * hd, hd, 0, _p(attn), H, _p(cu), _p(kvl), B, nh,

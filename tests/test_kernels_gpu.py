@@ -441,6 +441,38 @@ def test_attn_prefill_tcgen05(L, q_lens, pasts):
     _varlen_case(L, _call_tc(L), 128, True, q_lens, pasts, nh=2)
 
 
+def _call_tc2(L):
+    def fn(qkv, K, V, out, cu, past, N, B, nh, hd, cap, max_q, causal):
+        assert causal and hd == 128
+        H = nh * hd
+        L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), N, B, nh, cap, max_q, 1.0 / math.sqrt(hd), ST())
+    return fn
+
+
+@pytest.mark.parametrize("q_lens,pasts", [([128], [0]), ([256], [0]), ([146, 146], [0, 0]), ([607, 33, 129, 300], [0, 0, 0, 0]), ([19, 70], [27, 5]),
+                                          ([1587], [0]), ([300], [500])])
+def test_attn_prefill_tcgen05_pingpong(L, q_lens, pasts):
+    _varlen_case(L, _call_tc2(L), 128, True, q_lens, pasts, nh=2)
+
+
+def test_attn_prefill_pingpong_rescale_path(L):
+    """keys whose scores grow by far more than 2^8 along the sequence force the lazy O-rescale branch"""
+    B, nh, hd, Lq = 1, 1, 128, 512
+    H = nh * hd
+    qkv = torch.zeros(Lq, 3 * H, dtype=BF)
+    qkv[:, 0] = 8.0  # q = 8 * e0
+    K = torch.zeros(B, nh, Lq + 4, hd, dtype=BF)
+    V = rnd(B, nh, Lq + 4, hd, seed=95)
+    K[0, 0, :Lq, 0] = torch.linspace(-30, 30, Lq).to(BF)  # logits = 64 * k0 / sqrt(128): span ~ +-170
+    out = torch.zeros(Lq, H, device=DEV, dtype=BF)
+    cu = torch.tensor([0, Lq], dtype=torch.int32, device=DEV)
+    past = torch.zeros(1, dtype=torch.int32, device=DEV)
+    L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), Lq, B, nh, Lq + 4, Lq, 1.0 / math.sqrt(hd), ST())
+    torch.cuda.synchronize()
+    ref = _sdpa_ref(qkv[:, :hd], K[0, 0, :Lq], V[0, 0, :Lq], causal_off=0)
+    assert (out.float().cpu() - ref).abs().max() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
 # ---------------------------------------------------------------------------------------------- decode weight streaming
 @pytest.mark.parametrize("M,N,K,splits", [(8, 768, 256, 1), (8, 512, 512, 2), (1, 12288, 4096, 3), (8, 4096, 11008, 9), (16, 22016, 4096, 2),
                                           (3, 32000, 4096, 1), (24, 4096, 4096, 8), (64, 1024, 4096, 4)])
