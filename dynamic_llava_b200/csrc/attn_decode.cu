@@ -28,13 +28,29 @@ struct AdSmem {
   alignas(8) uint64_t empty[AD_STAGES];
   float m[AD_CWARPS], l[AD_CWARPS];
   float acc[AD_CWARPS][AD_HD];
+  float qs[AD_HD], kn[AD_HD], vn[AD_HD];  // fused mode: this (sample, head)'s rotated+scaled q and the new token's k, v
+};
+
+// Fused front end (decode step): the QKV projection arrives as the skinny GEMM's split-K slices; each (sample, head) CTA
+// sums ITS 3 x 128 values in fixed order, rounds to bf16 (nn.Linear output), applies RoPE with the reference's rounding
+// (dynamic_modeling_llama.py:253-285), keeps q/k_new/v_new in shared memory and — split 0 only — appends k/v to the arena
+// when the token is kept (cache_utils.py:153-241).  This removes the separate rope/append kernel from the step.
+struct AdFused {
+  const float* partial;  // [n_slices][B][3H] or null
+  int n_slices;
+  const int32_t* pos;    // [B]
+  const bf16* cos_t;
+  const bf16* sin_t;
+  const uint8_t* keep;   // [B] or null
+  bf16* k_arena_w;
+  bf16* v_arena_w;
 };
 
 __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     const bf16* __restrict__ q, int q_row_stride,  // q[b] at q + b*q_row_stride, [heads*128]
     const bf16* __restrict__ k_arena, const bf16* __restrict__ v_arena, const bf16* __restrict__ k_side,
     const bf16* __restrict__ v_side, const int32_t* __restrict__ kv_len, bf16* __restrict__ out, float* __restrict__ ws_acc,
-    float* __restrict__ ws_ml, int B, int heads, int cap, int n_split, float scale, int quirk_pad) {
+    float* __restrict__ ws_ml, int B, int heads, int cap, int n_split, float scale, int quirk_pad, const AdFused fz) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   AdSmem& S = *reinterpret_cast<AdSmem*>(smem_raw);
   const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
@@ -55,7 +71,60 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   const int k1 = min(len, k0 + kps);
   const int n_keys = max(k1 - k0, 0);
   const int n_tiles = (n_keys + AD_TK - 1) / AD_TK;
+  const bool fused = fz.partial != nullptr;
 
+  if (fused && threadIdx.x < 192) {
+    const int item = threadIdx.x >> 6, d = threadIdx.x & 63;  // 0 = q, 1 = k, 2 = v; dims d and d + 64
+    if (item == 0 || split == 0) {
+      const int H = heads * AD_HD;
+      const int64_t slice = (int64_t)B * 3 * H;
+      const float* base = fz.partial + (int64_t)b * 3 * H + (int64_t)item * H + h * AD_HD + d;
+      float x1 = 0.f, x2 = 0.f;
+      for (int s0 = 0; s0 < fz.n_slices; s0 += 8) {
+        float t1[8], t2[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (s0 + g < fz.n_slices) {
+            t1[g] = base[(int64_t)(s0 + g) * slice];
+            t2[g] = base[(int64_t)(s0 + g) * slice + 64];
+          }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (s0 + g < fz.n_slices) {
+            x1 += t1[g];
+            x2 += t2[g];
+          }
+      }
+      x1 = rbf(x1);
+      x2 = rbf(x2);
+      const bool persist = fz.keep == nullptr || fz.keep[b] != 0;
+      const int64_t arow = (((int64_t)b * heads + h) * cap + len) * AD_HD;
+      if (item < 2) {
+        const int p = fz.pos[b];
+        const float c = bf2f(fz.cos_t[(int64_t)p * AD_HD + d]), sn = bf2f(fz.sin_t[(int64_t)p * AD_HD + d]);
+        const float o1 = rbf(rbf(x1 * c) + rbf(-x2 * sn));
+        const float o2 = rbf(rbf(x2 * c) + rbf(x1 * sn));
+        if (item == 0) {
+          S.qs[d] = o1 * scale;
+          S.qs[d + 64] = o2 * scale;
+        } else {
+          S.kn[d] = o1;
+          S.kn[d + 64] = o2;
+          if (persist) {
+            fz.k_arena_w[arow + d] = f2bf(o1);
+            fz.k_arena_w[arow + d + 64] = f2bf(o2);
+          }
+        }
+      } else {
+        S.vn[d] = x1;
+        S.vn[d + 64] = x2;
+        if (persist) {
+          fz.v_arena_w[arow + d] = f2bf(x1);
+          fz.v_arena_w[arow + d + 64] = f2bf(x2);
+        }
+      }
+    }
+  }
   __syncthreads();
 
   const bf16* kbase = k_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
@@ -79,9 +148,14 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     // ---------------- consumer warps ----------------
     const int cidx = lane & 15, sub = lane >> 4;
     float qf[8];
-    unpack8(ld8(q + (int64_t)b * q_row_stride + h * AD_HD + cidx * 8), qf);
+    if (fused) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) qf[e] *= scale;
+      for (int e = 0; e < 8; ++e) qf[e] = S.qs[cidx * 8 + e];
+    } else {
+      unpack8(ld8(q + (int64_t)b * q_row_stride + h * AD_HD + cidx * 8), qf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qf[e] *= scale;
+    }
     float m_run = -INFINITY, l_run = 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -154,11 +228,16 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     }
 
     // the new token itself (side buffer); handled once, by warp 0 of split 0
-    if (warp == 0 && split == 0 && k_side != nullptr) {
+    if (warp == 0 && split == 0 && (fused || k_side != nullptr)) {
       float d = 0.f;
       if (sub == 0) {
         float kf[8];
-        unpack8(ld8(k_side + ((int64_t)b * heads + h) * AD_HD + cidx * 8), kf);
+        if (fused) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) kf[e] = S.kn[cidx * 8 + e];
+        } else {
+          unpack8(ld8(k_side + ((int64_t)b * heads + h) * AD_HD + cidx * 8), kf);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) d += qf[e] * kf[e];
       }
@@ -170,9 +249,15 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
       const float m_new = fmaxf(m_run, d);
       const float alpha = __expf(m_run - m_new);
       const float p = __expf(d - m_new);
-      const uint2 raw = *reinterpret_cast<const uint2*>(v_side + ((int64_t)b * heads + h) * AD_HD + lane * 4);
-      const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      float2 v01, v23;
+      if (fused) {
+        v01 = make_float2(S.vn[lane * 4], S.vn[lane * 4 + 1]);
+        v23 = make_float2(S.vn[lane * 4 + 2], S.vn[lane * 4 + 3]);
+      } else {
+        const uint2 raw = *reinterpret_cast<const uint2*>(v_side + ((int64_t)b * heads + h) * AD_HD + lane * 4);
+        v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      }
       acc[0] = acc[0] * alpha + p * v01.x;
       acc[1] = acc[1] * alpha + p * v01.y;
       acc[2] = acc[2] * alpha + p * v23.x;
@@ -259,11 +344,46 @@ extern "C" int dl_attn_decode(const void* q, int q_row_stride, const void* k_are
   }
   float* ws_acc = (float*)workspace;
   float* ws_ml = ws_acc ? ws_acc + (int64_t)B * heads * n_split * AD_HD : nullptr;
+  AdFused fz = {};
   dl_launch_pdl(attn_decode_kernel, dim3(heads, B, n_split), dim3(AD_THREADS), sizeof(AdSmem), stream, (const bf16*)q, q_row_stride,
                 (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)k_side, (const bf16*)v_side, kv_len, (bf16*)out, ws_acc, ws_ml,
-                B, heads, cap, n_split, scale, quirk_pad);
+                B, heads, cap, n_split, scale, quirk_pad, fz);
   if (n_split > 1)
     dl_launch_pdl(attn_decode_combine_kernel, dim3(heads, B), dim3(AD_HD), 0, stream, (const float*)ws_acc, (const float*)ws_ml,
                   (bf16*)out, heads, n_split);
   DL_CHECK_LAUNCH("dl_attn_decode");
+}
+
+// Decode step, fused: split-K QKV slices -> (reduce, RoPE, conditional append) -> ragged attention, one launch per layer.
+extern "C" int dl_attn_decode_fused(const float* qkv_partial, int n_slices, const int32_t* pos, const uint8_t* keep,
+                                    const void* cos_table, const void* sin_table, void* k_arena, void* v_arena,
+                                    const int32_t* kv_len, void* out, void* workspace, int B, int heads, int head_dim, int cap,
+                                    int n_split, float scale, int quirk_pad, cudaStream_t stream) {
+  DL_REQUIRE(head_dim == AD_HD && n_split >= 1 && (n_split == 1 || workspace != nullptr) && qkv_partial != nullptr,
+             "dl_attn_decode_fused");
+  if (B == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem));
+    if (e != cudaSuccess) return dl_set_error((int)e, "dl_attn_decode_fused(smem attr)");
+    attr_set = true;
+  }
+  float* ws_acc = (float*)workspace;
+  float* ws_ml = ws_acc ? ws_acc + (int64_t)B * heads * n_split * AD_HD : nullptr;
+  AdFused fz;
+  fz.partial = qkv_partial;
+  fz.n_slices = n_slices;
+  fz.pos = pos;
+  fz.cos_t = (const bf16*)cos_table;
+  fz.sin_t = (const bf16*)sin_table;
+  fz.keep = keep;
+  fz.k_arena_w = (bf16*)k_arena;
+  fz.v_arena_w = (bf16*)v_arena;
+  dl_launch_pdl(attn_decode_kernel, dim3(heads, B, n_split), dim3(AD_THREADS), sizeof(AdSmem), stream, (const bf16*)nullptr, 0,
+                (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)nullptr, (const bf16*)nullptr, kv_len, (bf16*)out, ws_acc, ws_ml,
+                B, heads, cap, n_split, scale, quirk_pad, fz);
+  if (n_split > 1)
+    dl_launch_pdl(attn_decode_combine_kernel, dim3(heads, B), dim3(AD_HD), 0, stream, (const float*)ws_acc, (const float*)ws_ml,
+                  (bf16*)out, heads, n_split);
+  DL_CHECK_LAUNCH("dl_attn_decode_fused");
 }

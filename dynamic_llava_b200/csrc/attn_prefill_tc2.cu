@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
   extern __shared__ uint8_t smem_raw[];
   T2Smem& S = *reinterpret_cast<T2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // causal: the last query tiles see the most keys -> schedule them first (longest-processing-time order)
+  const int mt = gridDim.x - 1 - blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q_start = cu_q[b];
   const int q_len = cu_q[b + 1] - q_start;
   const int m0 = mt * 256;

@@ -87,7 +87,7 @@ class Engine:
         if self.dtype != torch.bfloat16:
             raise RuntimeError("kernels compute in bf16: load the model with torch_dtype=torch.bfloat16")
         self.packed = None
-        self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc")  # "tc2" | "tc" (tcgen05 kernels) | "mma" (warp-MMA tile path)
+        self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc2")  # "tc2" | "tc" (tcgen05 kernels) | "mma" (warp-MMA tile path)
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.launches = 0  # kernels of OURS launched (eager path; graph replays counted via launches_per_step)
         self.launches_per_step = 0
@@ -484,13 +484,12 @@ class Engine:
             K_, V_, cap = a.layer(l)
             kvl = a.kv_len[l]
             s = self._gemm(sess, sess.xn, W["wqkv"], B, 3 * H, H)
-            L_.dec_reduce_rope_append(_p(sess.partial), s, _p(sess.q), _p(a.pos), _p(kvl), _p(keep if l >= SL else None),
-                                      _p(pk["cos"]), _p(pk["sin"]), _p(K_), _p(V_), _p(sess.k_side), _p(sess.v_side), B, nh, hd, cap, st)
             ns = self._n_split(B, nh, cap)
             if ns > 1 and sess.attn_ws is None:
                 sess.attn_ws = torch.empty(L_.attn_decode_workspace_bytes(B, nh, 16) // 4, device=self.device, dtype=torch.float32)
-            L_.attn_decode(_p(sess.q), H, _p(K_), _p(V_), _p(sess.k_side), _p(sess.v_side), _p(kvl), _p(sess.attn),
-                           _p(sess.attn_ws), B, nh, hd, cap, ns, scale, 1 if (quirk and l >= SL and keep is not None) else 0, st)
+            L_.attn_decode_fused(_p(sess.partial), s, _p(a.pos), _p(keep if l >= SL else None), _p(pk["cos"]), _p(pk["sin"]), _p(K_), _p(V_),
+                                 _p(kvl), _p(sess.attn), _p(sess.attn_ws), B, nh, hd, cap, ns, scale,
+                                 1 if (quirk and l >= SL and keep is not None) else 0, st)
             s = self._gemm(sess, sess.attn, W["wo"], B, H, H)
             L_.dec_reduce_residual_norm(_p(sess.partial), _p(sess.xres), _p(W["ln2"]), _p(sess.xn), B, H, s, eps, st)
             s = self._gemm(sess, sess.xn, W["wgu"], B, 2 * I, H)
@@ -498,7 +497,7 @@ class Engine:
             s = self._gemm(sess, sess.act, W["wd"], B, H, I)
             nxt = pk["layers"][l + 1]["ln1"] if l + 1 < Lyr else m.norm.weight
             L_.dec_reduce_residual_norm(_p(sess.partial), _p(sess.xres), _p(nxt), _p(sess.xn), B, H, s, eps, st)
-            self.launches += 5 + (2 if ns > 1 else 1)
+            self.launches += 4 + (2 if ns > 1 else 1)
         s = self._gemm(sess, sess.xn, self.model.lm_head.weight, B, V, H)
         L_.dec_reduce_bf16(_p(sess.partial), _p(sess.logits), B, V, s, st)
         self.launches += 1

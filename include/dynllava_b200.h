@@ -98,6 +98,12 @@ int dl_attn_decode(const void* q, int q_row_stride, const void* k_arena, const v
                    const void* v_side, const int32_t* kv_len, void* out, void* workspace, int B, int heads, int head_dim,
                    int cap, int n_split, float scale, int quirk_pad, cudaStream_t stream);
 
+/* K3 + K4 + K5 fused for the decode step: reads the QKV projection as split-K slices partial[n_slices][B][3H], does the
+ * reduce + bf16 rounding + RoPE + conditional append per (sample, head) inside the attention CTA (DML:1011-1083). */
+int dl_attn_decode_fused(const float* qkv_partial, int n_slices, const int32_t* pos, const uint8_t* keep, const void* cos_table,
+                         const void* sin_table, void* k_arena, void* v_arena, const int32_t* kv_len, void* out, void* workspace,
+                         int B, int heads, int head_dim, int cap, int n_split, float scale, int quirk_pad, cudaStream_t stream);
+
 /* ---- K2/K6/K7: variable-length attention (warp-MMA tile path), DML:1114-1122; CTL:164-169; HF CLIPAttention ---- */
 /* Addresses: Q(b,i,h) = q + (cu_q[b]+i)*q_tok_stride + h*q_head_stride;
  * K(b,j,h) = k + b*kv_batch_stride + h*kv_head_stride + ((kv_packed ? cu_q[b] : 0) + j)*kv_tok_stride (V alike);

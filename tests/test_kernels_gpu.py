@@ -359,6 +359,42 @@ def test_attn_decode(L, lens, n_split, quirk):
             assert (got - ref).abs().max() < 2e-2 * max(1.0, ref.abs().max()), (b, h, (got - ref).abs().max())
 
 
+@pytest.mark.parametrize("lens,n_split,S,quirk", [([146, 210, 64, 1], 1, 3, 0), ([735, 650, 129, 300], 2, 2, 0), ([40, 70, 70, 3], 1, 1, 1)])
+def test_attn_decode_fused_equals_unfused(L, lens, n_split, S, quirk):
+    """dl_attn_decode_fused (reduce + RoPE + append inside the attention CTA) must be bit-identical to
+    dl_dec_reduce_rope_append followed by dl_attn_decode, including the arena contents."""
+    B, nh, hd = len(lens), 4, 128
+    H = nh * hd
+    cap = max(lens) + 8
+    K = torch.zeros(B, nh, cap, hd, dtype=BF)
+    V = torch.zeros_like(K)
+    for b, n in enumerate(lens):
+        K[b, :, :n] = rnd(nh, n, hd, seed=230 + b)
+        V[b, :, :n] = rnd(nh, n, hd, seed=240 + b)
+    part = rnd(S, B, 3 * H, seed=250, dtype=torch.float32).to(DEV)
+    cos, sin = O.rope_tables(hd, 4096, 10000.0, BF)
+    cos, sin = cos.to(DEV), sin.to(DEV)
+    pos = torch.tensor([n + 400 for n in lens], dtype=torch.int32, device=DEV)
+    kvl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    keep = torch.tensor([1, 0, 1, 0], dtype=torch.uint8, device=DEV)
+    sc = 1.0 / math.sqrt(hd)
+    ws = torch.empty(max(L.attn_decode_workspace_bytes(B, nh, n_split) // 4, 1), device=DEV, dtype=torch.float32)
+    K1, V1 = K.to(DEV).clone(), V.to(DEV).clone()
+    q = torch.empty(B, H, device=DEV, dtype=BF)
+    ks, vs = torch.empty(B, nh, hd, device=DEV, dtype=BF), torch.empty(B, nh, hd, device=DEV, dtype=BF)
+    o1 = torch.empty(B, H, device=DEV, dtype=BF)
+    L.dec_reduce_rope_append(P(part), S, P(q), P(pos), P(kvl), P(keep), P(cos), P(sin), P(K1), P(V1), P(ks), P(vs), B, nh, hd, cap, ST())
+    L.attn_decode(P(q), H, P(K1), P(V1), P(ks), P(vs), P(kvl), P(o1), P(ws), B, nh, hd, cap, n_split, sc, quirk, ST())
+    K2, V2 = K.to(DEV).clone(), V.to(DEV).clone()
+    o2 = torch.empty(B, H, device=DEV, dtype=BF)
+    L.attn_decode_fused(P(part), S, P(pos), P(keep), P(cos), P(sin), P(K2), P(V2), P(kvl), P(o2), P(ws), B, nh, hd, cap, n_split, sc, quirk, ST())
+    torch.cuda.synchronize()
+    assert torch.equal(K1, K2) and torch.equal(V1, V2)
+    assert torch.equal(o1, o2), (o1.float() - o2.float()).abs().max()
+    for b in range(B):  # appended iff kept, at slot len_b
+        assert bool((K2[b, :, lens[b]] != 0).any()) == bool(keep[b])
+
+
 def _varlen_case(L, fn, hd, causal, q_lens, pasts, nh=3):
     """build arena-layout K/V with `past` cached keys + the new q_len keys; compare with fp32 attention per sample"""
     B = len(q_lens)
