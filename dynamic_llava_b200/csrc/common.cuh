@@ -197,6 +197,10 @@ DL_DEVINL void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// L2 prefetch of one tensor-map box (no shared memory, no barrier): starts the HBM -> L2 stream early
+DL_DEVINL void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 DL_DEVINL void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

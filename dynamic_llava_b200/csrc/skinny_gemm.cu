@@ -33,7 +33,7 @@ template <int NB>
 __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                                  const __grid_constant__ CUtensorMap tmap_x,
                                                                  float* __restrict__ partial, int M, int N, int KB,
-                                                                 int kb_per_split) {
+                                                                 int kb_per_split, int l2_pf) {
   constexpr int TM_COLS = NB < 32 ? 32 : NB;
   extern __shared__ uint8_t smem_raw[];
   SgSmem<NB>& S = *reinterpret_cast<SgSmem<NB>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -70,6 +70,10 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
         mbar_expect_tx(&S.full[i], BYTES);
         tma_load_2d(S.a[i], &tmap_w, (kb0 + i) * SG_BK, n0, &S.full[i]);
       }
+      // ...and ask the TMA unit to pull the next `l2_pf` W tiles of this CTA into the 126 MB L2 (no smem needed), so HBM
+      // keeps streaming weights while the small predecessor kernel (norm / SwiGLU / attention) is still running.
+      const int npf = min(nkb, npre + l2_pf);
+      for (int i = npre; i < npf; ++i) tma_prefetch_2d(&tmap_w, (kb0 + i) * SG_BK, n0);
       pdl_launch_dependents();
       pdl_wait();
       for (int i = 0; i < npre; ++i) tma_load_2d(S.b[i], &tmap_x, (kb0 + i) * SG_BK, 0, &S.full[i]);
@@ -160,7 +164,7 @@ extern "C" int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, u
 
 template <int NB>
 static int launch_sg(const CUtensorMap& tw, const CUtensorMap& tx, float* partial, int M, int N, int KB, int splits, int kbps,
-                     cudaStream_t stream) {
+                     int l2_prefetch_mb, cudaStream_t stream) {
   const int smem = (int)sizeof(SgSmem<NB>) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -169,7 +173,9 @@ static int launch_sg(const CUtensorMap& tw, const CUtensorMap& tx, float* partia
     attr_set = true;
   }
   dim3 grid((N + SG_BM - 1) / SG_BM, splits);
-  cudaError_t le = dl_launch_pdl(skinny_gemm_kernel<NB>, grid, dim3(SG_THREADS), (size_t)smem, stream, tw, tx, partial, M, N, KB, kbps);
+  const int64_t budget = (int64_t)(l2_prefetch_mb < 0 ? 0 : l2_prefetch_mb) << 20;  // total bytes prefetched ahead into L2 (default: off)
+  const int l2_pf = (int)(budget / ((int64_t)grid.x * grid.y * SG_BM * SG_BK * 2));
+  cudaError_t le = dl_launch_pdl(skinny_gemm_kernel<NB>, grid, dim3(SG_THREADS), (size_t)smem, stream, tw, tx, partial, M, N, KB, kbps, l2_pf);
   if (le != cudaSuccess) return dl_set_error((int)le, "dl_skinny_gemm(launch)");
   DL_CHECK_LAUNCH("dl_skinny_gemm");
 }
@@ -187,7 +193,7 @@ extern "C" int dl_skinny_gemm_splits(int N, int K, int target_ctas) {
   return (KB + kbps - 1) / kbps;  // effective number of non-empty splits
 }
 
-extern "C" int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits,
+extern "C" int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits, int l2_prefetch_mb,
                               cudaStream_t stream) {
   DL_REQUIRE(M >= 1 && M <= 64 && K % SG_BK == 0 && N % 8 == 0 && splits >= 1, "dl_skinny_gemm");
   const int KB = K / SG_BK;
@@ -199,7 +205,7 @@ extern "C" int dl_skinny_gemm(const void* x, const void* w, float* partial, int 
   if (rc) return rc;
   rc = dl_make_tmap_2d(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)K, (uint32_t)NB, SG_BK);
   if (rc) return rc;
-  if (NB == 16) return launch_sg<16>(tw, tx, partial, M, N, KB, splits, kbps, stream);
-  if (NB == 32) return launch_sg<32>(tw, tx, partial, M, N, KB, splits, kbps, stream);
-  return launch_sg<64>(tw, tx, partial, M, N, KB, splits, kbps, stream);
+  if (NB == 16) return launch_sg<16>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, stream);
+  if (NB == 32) return launch_sg<32>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, stream);
+  return launch_sg<64>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, stream);
 }

@@ -89,6 +89,7 @@ class Engine:
         self.packed = None
         self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc2")  # "tc2" | "tc" (tcgen05 kernels) | "mma" (warp-MMA tile path)
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
+        self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
         self.launches = 0  # kernels of OURS launched (eager path; graph replays counted via launches_per_step)
         self.launches_per_step = 0
 
@@ -444,7 +445,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------------------------
     def _gemm(self, sess, x, w, M, N, K):
         s = self.L.skinny_gemm_splits(N, K, self.skinny_target_ctas)
-        self.L.skinny_gemm(_p(x), _p(w), _p(sess.partial), M, N, K, s, _stream())
+        self.L.skinny_gemm(_p(x), _p(w), _p(sess.partial), M, N, K, s, self.l2_prefetch_mb, _stream())
         self.launches += 1
         return s
 

@@ -124,9 +124,12 @@ int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena
                         int cap, int max_q_len, float scale, cudaStream_t stream);
 
 /* ---- decode-step weight streaming: every nn.Linear at q_len == 1 (DML:1011-1013, :1127, :328, :2709) ----------- */
-/* partial fp32 [splits, M, N] = per-split X[M,K] . W[N,K]^T; M <= 64, K % 64 == 0.  TMA + tcgen05. */
+/* partial fp32 [splits, M, N] = per-split X[M,K] . W[N,K]^T; M <= 64, K % 64 == 0.  TMA + tcgen05.
+ * l2_prefetch_mb: bytes of W (total over the grid) each launch asks the TMA unit to pull into L2 ahead of its smem ring
+ * while it still waits (PDL) for its predecessor; <= 0 = off (default: measured slower on B200, profiles/r1_l2_prefetch_sweep.md). */
 int dl_skinny_gemm_splits(int N, int K, int target_ctas);
-int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits, cudaStream_t stream);
+int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits, int l2_prefetch_mb,
+                   cudaStream_t stream);
 int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                     uint32_t box_rows, uint32_t box_cols);
 int dl_dec_reduce_bf16(const float* partial, void* y, int M, int N, int splits, cudaStream_t stream);

@@ -515,7 +515,7 @@ def test_attn_prefill_pingpong_rescale_path(L):
 def test_skinny_gemm_tcgen05(L, M, N, K, splits):
     x, w = rnd(M, K, seed=100), rnd(N, K, seed=101, scale=0.05)
     part = torch.full((splits, M, N), float("nan"), device=DEV, dtype=torch.float32)
-    L.skinny_gemm(P(x.to(DEV)), P(w.to(DEV)), P(part), M, N, K, splits, ST())
+    L.skinny_gemm(P(x.to(DEV)), P(w.to(DEV)), P(part), M, N, K, splits, -1 if splits % 2 else 0, ST())
     torch.cuda.synchronize()
     got = part.sum(0).cpu()
     ref = x.float() @ w.float().T

@@ -162,13 +162,20 @@ def bench_skinny(out):
         Ws = [torch.randn(N, K, device=DEV, dtype=BF) for _ in range(n_rot)]
         x = torch.randn(M, K, device=DEV, dtype=BF)
         best = None
-        for tgt in (148, 222, 296, 444, 592):
-            s = L.skinny_gemm_splits(N, K, tgt)
+        allv = {}
+        KB = K // 64
+        for s in (1, 2, 3, 4, 6, 8):
+            kbps = -(-KB // s)
+            if (s - 1) * kbps >= KB or kbps < 4:
+                continue
             part = torch.empty(s, M, N, device=DEV, dtype=torch.float32)
-            ms = timeit(lambda i: L.skinny_gemm(P(x), P(Ws[i]), P(part), M, N, K, s, ST()), n_rot)
+            ms = timeit(lambda i: L.skinny_gemm(P(x), P(Ws[i]), P(part), M, N, K, s, 0, ST()), n_rot)
             gbs = N * K * 2 / ms / 1e6
+            allv[s] = round(ms * 1e3, 2)
             if best is None or gbs > best["GBps"]:
-                best = {"target_ctas": tgt, "splits": s, "us": ms * 1e3, "GBps": gbs}
+                best = {"splits": s, "us": ms * 1e3, "GBps": gbs}
+        best["all_splits_us"] = allv
+        best["heuristic_splits"] = L.skinny_gemm_splits(N, K, 296)
         import torch.nn.functional as F
         ms_c = timeit(lambda i: F.linear(x, Ws[i]), n_rot)
         rows.append({"case": name, "MB": N * K * 2 / 1e6, **best, "frac_of_measured_hbm": best["GBps"] / pk, "cublas_us": ms_c * 1e3,
