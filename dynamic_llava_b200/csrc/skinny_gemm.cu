@@ -184,6 +184,7 @@ extern "C" int dl_skinny_gemm_splits(int N, int K, int target_ctas) {
   const int tiles = (N + SG_BM - 1) / SG_BM;
   const int KB = K / SG_BK;
   int s = (target_ctas + tiles / 2) / tiles;
+  if (tiles >= 148) s = 1;  // one full wave of row tiles already: splitting K only adds slices (measured: profiles/r1_microbench_v4_skinny_splits.json)
   if (s < 1) s = 1;
   int max_s = KB / 4;  // keep >= 4 k-blocks (64 KB of W) per CTA
   if (max_s < 1) max_s = 1;
