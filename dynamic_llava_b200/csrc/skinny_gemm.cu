@@ -29,16 +29,21 @@ struct SgSmem {
   uint32_t tmem_base;
 };
 
-template <int NB>
+// EPI == 0: fp32 split-K slices.  EPI == 1 (gate|up projection, splits == 1): each 128-row A tile is assembled from TWO
+// 64-row TMA boxes — gate rows [64j, 64j+64) and the matching up rows [I+64j, I+64j+64) of the same fused [2I, K] weight the
+// prefill uses — so one tile holds both halves of 64 SwiGLU outputs; the epilogue exchanges the `up` half through shared
+// memory and writes act = bf16(bf16(silu(bf16 g)) * bf16 u) directly (dynamic_modeling_llama.py:328): no slice round trip
+// and no separate SwiGLU kernel in the decode step.
+template <int NB, int EPI>
 __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                                  const __grid_constant__ CUtensorMap tmap_x,
                                                                  float* __restrict__ partial, int M, int N, int KB,
-                                                                 int kb_per_split, int l2_pf) {
+                                                                 int kb_per_split, int l2_pf, bf16* __restrict__ act_out) {
   constexpr int TM_COLS = NB < 32 ? 32 : NB;
   extern __shared__ uint8_t smem_raw[];
   SgSmem<NB>& S = *reinterpret_cast<SgSmem<NB>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * SG_BM;
+  const int n0 = blockIdx.x * SG_BM;  // EPI == 1: tile j = blockIdx.x covers SwiGLU outputs [64j, 64j+64)
   const int split = blockIdx.y;
   const int kb0 = split * kb_per_split;
   const int kb1 = min(KB, kb0 + kb_per_split);
@@ -66,14 +71,23 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
       // The weights do not depend on the previous kernel: start streaming W into every free stage right away, and only
       // then wait for the predecessor (PDL) before fetching the activation tiles X it produced.
       const int npre = min(nkb, SG_STAGES);
+      const int I_rows = N >> 1, g0 = blockIdx.x * 64;
+      auto load_w = [&](int stage, int kb) {
+        if constexpr (EPI == 1) {  // tmap_w box = 64 rows: gate half then up half (8 KB apart keeps the 128B swizzle phase)
+          tma_load_2d(S.a[stage], &tmap_w, kb * SG_BK, g0, &S.full[stage]);
+          tma_load_2d(S.a[stage] + 64 * SG_BK, &tmap_w, kb * SG_BK, I_rows + g0, &S.full[stage]);
+        } else {
+          tma_load_2d(S.a[stage], &tmap_w, kb * SG_BK, n0, &S.full[stage]);
+        }
+      };
       for (int i = 0; i < npre; ++i) {
         mbar_expect_tx(&S.full[i], BYTES);
-        tma_load_2d(S.a[i], &tmap_w, (kb0 + i) * SG_BK, n0, &S.full[i]);
+        load_w(i, kb0 + i);
       }
       // ...and ask the TMA unit to pull the next `l2_pf` W tiles of this CTA into the 126 MB L2 (no smem needed), so HBM
       // keeps streaming weights while the small predecessor kernel (norm / SwiGLU / attention) is still running.
       const int npf = min(nkb, npre + l2_pf);
-      for (int i = npre; i < npf; ++i) tma_prefetch_2d(&tmap_w, (kb0 + i) * SG_BK, n0);
+      for (int i = npre; i < npf; ++i) tma_prefetch_2d(&tmap_w, (kb0 + i) * SG_BK, EPI == 1 ? g0 : n0);
       pdl_launch_dependents();
       pdl_wait();
       for (int i = 0; i < npre; ++i) tma_load_2d(S.b[i], &tmap_x, (kb0 + i) * SG_BK, 0, &S.full[i]);
@@ -82,7 +96,7 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
         const uint32_t ph = (i / SG_STAGES) & 1;
         mbar_wait(&S.empty[s], ph ^ 1);
         mbar_expect_tx(&S.full[s], BYTES);
-        tma_load_2d(S.a[s], &tmap_w, (kb0 + i) * SG_BK, n0, &S.full[s]);
+        load_w(s, kb0 + i);
         tma_load_2d(S.b[s], &tmap_x, (kb0 + i) * SG_BK, 0, &S.full[s]);
       }
     }
@@ -108,7 +122,34 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int n = n0 + q * 32 + lane;
     float* dst = partial + (int64_t)split * M * N + n;
-    if (nkb > 0) {
+    if constexpr (EPI == 1) {
+      float* xch = reinterpret_cast<float*>(S.a[0]);  // [64 rows][NB] floats; every stage has been consumed by now
+      mbar_wait(&S.tmem_full, 0);
+      tc_fence_after();
+      uint32_t r[NB];
+#pragma unroll
+      for (int c0 = 0; c0 < NB; c0 += 16) tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r + c0);
+      tmem_ld_wait();
+      const int row = (q & 1) * 32 + lane;  // index inside the 64-row half
+      if (q >= 2) {
+#pragma unroll
+        for (int m = 0; m < NB; ++m) xch[row * NB + m] = __uint_as_float(r[m]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      if (q < 2) {
+        const int I = N >> 1;
+        const int col = blockIdx.x * 64 + row;
+        if (col < I) {
+#pragma unroll
+          for (int m = 0; m < NB; ++m) {
+            if (m < M) {
+              const float g = rbf(__uint_as_float(r[m])), u = rbf(xch[row * NB + m]);
+              act_out[(int64_t)m * I + col] = f2bf(rbf(g / (1.0f + expf(-g))) * u);
+            }
+          }
+        }
+      }
+    } else if (nkb > 0) {
       mbar_wait(&S.tmem_full, 0);
       tc_fence_after();
 #pragma unroll
@@ -162,20 +203,21 @@ extern "C" int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, u
   return 0;
 }
 
-template <int NB>
+template <int NB, int EPI>
 static int launch_sg(const CUtensorMap& tw, const CUtensorMap& tx, float* partial, int M, int N, int KB, int splits, int kbps,
-                     int l2_prefetch_mb, cudaStream_t stream) {
+                     int l2_prefetch_mb, bf16* act_out, cudaStream_t stream) {
   const int smem = (int)sizeof(SgSmem<NB>) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel<NB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return dl_set_error((int)e, "dl_skinny_gemm(smem attr)");
     attr_set = true;
   }
   dim3 grid((N + SG_BM - 1) / SG_BM, splits);
   const int64_t budget = (int64_t)(l2_prefetch_mb < 0 ? 0 : l2_prefetch_mb) << 20;  // total bytes prefetched ahead into L2 (default: off)
   const int l2_pf = (int)(budget / ((int64_t)grid.x * grid.y * SG_BM * SG_BK * 2));
-  cudaError_t le = dl_launch_pdl(skinny_gemm_kernel<NB>, grid, dim3(SG_THREADS), (size_t)smem, stream, tw, tx, partial, M, N, KB, kbps, l2_pf);
+  cudaError_t le = dl_launch_pdl(skinny_gemm_kernel<NB, EPI>, grid, dim3(SG_THREADS), (size_t)smem, stream, tw, tx, partial, M, N, KB, kbps,
+                                 l2_pf, act_out);
   if (le != cudaSuccess) return dl_set_error((int)le, "dl_skinny_gemm(launch)");
   DL_CHECK_LAUNCH("dl_skinny_gemm");
 }
@@ -206,7 +248,23 @@ extern "C" int dl_skinny_gemm(const void* x, const void* w, float* partial, int 
   if (rc) return rc;
   rc = dl_make_tmap_2d(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)K, (uint32_t)NB, SG_BK);
   if (rc) return rc;
-  if (NB == 16) return launch_sg<16>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, stream);
-  if (NB == 32) return launch_sg<32>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, stream);
-  return launch_sg<64>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, stream);
+  if (NB == 16) return launch_sg<16, 0>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, nullptr, stream);
+  if (NB == 32) return launch_sg<32, 0>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, nullptr, stream);
+  return launch_sg<64, 0>(tw, tx, partial, M, N, KB, splits, kbps, l2_prefetch_mb, nullptr, stream);
+}
+
+// gate|up projection + SwiGLU in one launch.  w_gate_up [2I, K] = [gate rows | up rows]; act_out bf16 [M, I].
+extern "C" int dl_skinny_gemm_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K,
+                                     cudaStream_t stream) {
+  DL_REQUIRE(M >= 1 && M <= 64 && K % SG_BK == 0 && I % 64 == 0, "dl_skinny_gemm_swiglu");
+  const int N = 2 * I, KB = K / SG_BK;
+  const int NB = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  alignas(64) CUtensorMap tw, tx;
+  int rc = dl_make_tmap_2d(&tw, w_gate_up, (uint64_t)N, (uint64_t)K, (uint64_t)K, 64, SG_BK);  // 64-row boxes
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)K, (uint32_t)NB, SG_BK);
+  if (rc) return rc;
+  if (NB == 16) return launch_sg<16, 1>(tw, tx, nullptr, M, N, KB, 1, KB, 0, (bf16*)act_out, stream);
+  if (NB == 32) return launch_sg<32, 1>(tw, tx, nullptr, M, N, KB, 1, KB, 0, (bf16*)act_out, stream);
+  return launch_sg<64, 1>(tw, tx, nullptr, M, N, KB, 1, KB, 0, (bf16*)act_out, stream);
 }

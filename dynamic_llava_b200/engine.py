@@ -493,12 +493,11 @@ class Engine:
                                  1 if (quirk and l >= SL and keep is not None) else 0, st)
             s = self._gemm(sess, sess.attn, W["wo"], B, H, H)
             L_.dec_reduce_residual_norm(_p(sess.partial), _p(sess.xres), _p(W["ln2"]), _p(sess.xn), B, H, s, eps, st)
-            s = self._gemm(sess, sess.xn, W["wgu"], B, 2 * I, H)
-            L_.dec_reduce_swiglu(_p(sess.partial), _p(sess.act), B, I, s, st)
+            L_.skinny_gemm_swiglu(_p(sess.xn), _p(W["wgu"]), _p(sess.act), B, I, H, st)  # gate|up GEMM with SwiGLU in the epilogue
             s = self._gemm(sess, sess.act, W["wd"], B, H, I)
             nxt = pk["layers"][l + 1]["ln1"] if l + 1 < Lyr else m.norm.weight
             L_.dec_reduce_residual_norm(_p(sess.partial), _p(sess.xres), _p(nxt), _p(sess.xn), B, H, s, eps, st)
-            self.launches += 4 + (2 if ns > 1 else 1)
+            self.launches += 4 + (2 if ns > 1 else 1)  # + 3 split-K GEMMs counted in _gemm
         s = self._gemm(sess, sess.xn, self.model.lm_head.weight, B, V, H)
         L_.dec_reduce_bf16(_p(sess.partial), _p(sess.logits), B, V, s, st)
         self.launches += 1

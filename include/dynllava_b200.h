@@ -130,6 +130,10 @@ int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena
 int dl_skinny_gemm_splits(int N, int K, int target_ctas);
 int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits, int l2_prefetch_mb,
                    cudaStream_t stream);
+/* gate|up projection with the SwiGLU fused into the TMEM epilogue (DML:328 at q_len == 1).  w_gate_up [2I,K] = [gate rows | up
+ * rows] (the same fused weight the prefill uses): each CTA tile is assembled from 64 gate rows + the 64 matching up rows by
+ * two TMA boxes; act_out bf16 [M, I]. */
+int dl_skinny_gemm_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K, cudaStream_t stream);
 int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                     uint32_t box_rows, uint32_t box_cols);
 int dl_dec_reduce_bf16(const float* partial, void* y, int M, int N, int splits, cudaStream_t stream);

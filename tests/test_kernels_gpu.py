@@ -524,6 +524,24 @@ def test_skinny_gemm_tcgen05(L, M, N, K, splits):
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err  # fp32 accumulation of exact bf16 products
 
 
+@pytest.mark.parametrize("M,I,K", [(8, 512, 256), (8, 11008, 4096), (3, 13824, 5120), (24, 1024, 512)])
+def test_skinny_gemm_swiglu_epilogue(L, M, I, K):
+    """gate|up GEMM with SwiGLU fused into the TMEM epilogue == split-K GEMM + dl_dec_reduce_swiglu (same fp32 sums)."""
+    x, w = rnd(M, K, seed=140), rnd(2 * I, K, seed=141, scale=0.05)
+    xd, wd = x.to(DEV), w.to(DEV)
+    act = torch.empty(M, I, device=DEV, dtype=BF)
+    L.skinny_gemm_swiglu(P(xd), P(wd), P(act), M, I, K, ST())
+    part = torch.empty(1, M, 2 * I, device=DEV, dtype=torch.float32)
+    L.skinny_gemm(P(xd), P(wd), P(part), M, 2 * I, K, 1, 0, ST())
+    ref = torch.empty(M, I, device=DEV, dtype=BF)
+    L.dec_reduce_swiglu(P(part), P(ref), M, I, 1, ST())
+    torch.cuda.synchronize()
+    assert torch.equal(act, ref), (act.float() - ref.float()).abs().max()
+    gu = (x.float() @ w.float().T)
+    want = (F.silu(gu[:, :I].to(BF)) * gu[:, I:].to(BF)).float()
+    assert (act.float().cpu() - want).abs().max() < 2e-2 * max(1.0, want.abs().max().item())
+
+
 def test_skinny_gemm_split_heuristic(L):
     for N, K in [(12288, 4096), (4096, 4096), (22016, 4096), (4096, 11008), (32000, 4096), (512, 4096), (768, 256)]:
         s = L.skinny_gemm_splits(N, K, 296)
