@@ -78,12 +78,13 @@ def config4(out, batch=4):
     fd = forced_text_decisions(1, batch, 0.5, seed=3)
     kw = dict(images=pix, do_sample=False, eos_token_id=None)
     t_pre = timed(lambda: model.generate(ids, max_new_tokens=1, **kw), reps=3, warm=1)
-    t_2 = timed(lambda: model.generate(ids, max_new_tokens=2, forced_text_decisions=fd, **kw), reps=3, warm=1)
+    fd = forced_text_decisions(16, batch, 0.5, seed=3)
+    t_2 = timed(lambda: model.generate(ids, max_new_tokens=17, forced_text_decisions=fd, **kw), reps=3, warm=1)
     sess = next(iter(model._sessions.values()))
     lens = sess.arena.kv_len.cpu()
     out["config4_13b_prefill2048"] = {"model": "llava-1.5-13b", "batch_per_gpu": batch, "P": 2048, "P_prime": 2048 - 576 + 115,
                                       "clip_prefill_ms": t_pre, "prefill_tokens_per_s": batch * 2048 / (t_pre / 1e3),
-                                      "first_decode_step_ms": t_2 - t_pre, "kv_len_layer0": lens[0].tolist(), "kv_len_last": lens[-1].tolist()}
+                                      "decode_ms_per_step": (t_2 - t_pre) / 16, "kv_len_layer0": lens[0].tolist(), "kv_len_last": lens[-1].tolist()}
     print("CFG4", out["config4_13b_prefill2048"], flush=True)
 
 
