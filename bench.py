@@ -250,7 +250,10 @@ def phase_and_roofline(model, eng, a, ids_d, pix_d, fd, dev):
         "phases": {"clip_prefill_ms": prefill_ms, "prefill_tokens_per_s": B * 607 / (prefill_ms / 1e3),
                    "decode_ms_per_token_step": None, "weight_gemm_ms_per_decode_step": gemm_ms},
         "roofline": {"bound": "hbm", "kernel": "skinny_gemm_kernel (decode weight streaming, TMA+tcgen05)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": 1.033 * bytes_total / len(shapes),
+                     "traffic_source": "ncu --set full, QKV launch: dram read+write 104.88 MB vs 101.5 MB algorithmic (x1.033), "
+                                       "scaled to this step's average launch (profiles/r1_ncu_skinny_gemm_full.md)",
+                     "peak_source": how,
                      "algorithmic_bytes_per_launch": bytes_total / len(shapes), "launches_per_decode_step": len(shapes),
                      "avg_launch_us": gemm_ms * 1e3 / len(shapes)},
     }

@@ -25,7 +25,6 @@ SOURCES = [
     "attn_prefill_mma.cu",
     "attn_prefill_tc.cu",
     "attn_prefill_tc2.cu",
-    "attn_prefill_tc3.cu",
     "skinny_gemm.cu",
     "decode_fused.cu",
     "predictor_ops.cu",

@@ -366,9 +366,7 @@ class Engine:
                            None, None, N, B, nh, hd, cap, _stream())
         attn = torch.empty(N, H, device=x.device, dtype=x.dtype)
         scale = 1.0 / math.sqrt(hd)
-        if self.prefill_attn == "tc3":
-            self.L.attn_prefill_tc3(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())
-        elif self.prefill_attn == "tc2":
+        if self.prefill_attn == "tc2":
             self.L.attn_prefill_tc2(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())
         elif self.prefill_attn == "tc":
             self.L.attn_prefill_tc(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())

@@ -123,11 +123,6 @@ int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena
                         int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
                         int cap, int max_q_len, float scale, cudaStream_t stream);
 
-/* K2 v3: v2 with two threads per query row (576-thread CTAs) — the default prefill attention (attn_prefill_tc3.cu). */
-int dl_attn_prefill_tc3(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
-                        int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
-                        int cap, int max_q_len, float scale, cudaStream_t stream);
-
 /* ---- decode-step weight streaming: every nn.Linear at q_len == 1 (DML:1011-1013, :1127, :328, :2709) ----------- */
 /* partial fp32 [splits, M, N] = per-split X[M,K] . W[N,K]^T; M <= 64, K % 64 == 0.  TMA + tcgen05.
  * l2_prefetch_mb: bytes of W (total over the grid) each launch asks the TMA unit to pull into L2 ahead of its smem ring

@@ -491,21 +491,7 @@ def test_attn_prefill_tcgen05_pingpong(L, q_lens, pasts):
     _varlen_case(L, _call_tc2(L), 128, True, q_lens, pasts, nh=2)
 
 
-def _call_tc3(L):
-    def fn(qkv, K, V, out, cu, past, N, B, nh, hd, cap, max_q, causal):
-        assert causal and hd == 128
-        H = nh * hd
-        L.attn_prefill_tc3(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), N, B, nh, cap, max_q, 1.0 / math.sqrt(hd), ST())
-    return fn
-
-
-@pytest.mark.parametrize("q_lens,pasts", [([128], [0]), ([256], [0]), ([146, 146], [0, 0]), ([607, 33, 129, 300], [0, 0, 0, 0]), ([19, 70], [27, 5]),
-                                          ([1587], [0]), ([300], [500])])
-def test_attn_prefill_tcgen05_two_threads_per_row(L, q_lens, pasts):
-    _varlen_case(L, _call_tc3(L), 128, True, q_lens, pasts, nh=2)
-
-
-@pytest.mark.parametrize("which", ["tc2", "tc3"])
+@pytest.mark.parametrize("which", ["tc2"])
 def test_attn_prefill_pingpong_rescale_path(L, which):
     """keys whose scores grow by far more than 2^8 along the sequence force the lazy O-rescale branch"""
     B, nh, hd, Lq = 1, 1, 128, 512
@@ -518,7 +504,7 @@ def test_attn_prefill_pingpong_rescale_path(L, which):
     out = torch.zeros(Lq, H, device=DEV, dtype=BF)
     cu = torch.tensor([0, Lq], dtype=torch.int32, device=DEV)
     past = torch.zeros(1, dtype=torch.int32, device=DEV)
-    fn = L.attn_prefill_tc2 if which == "tc2" else L.attn_prefill_tc3
+    fn = L.attn_prefill_tc2
     fn(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), Lq, B, nh, Lq + 4, Lq, 1.0 / math.sqrt(hd), ST())
     torch.cuda.synchronize()
     ref = _sdpa_ref(qkv[:, :hd], K[0, 0, :Lq], V[0, 0, :Lq], causal_off=0)

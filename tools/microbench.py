@@ -114,8 +114,6 @@ def bench_attn_prefill(out):
         o_tc = o.clone()
         ms_tc2 = timeit(lambda i: L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, ST()), 1)
         diff2 = (o.float() - o_tc.float()).abs().max().item()
-        ms_tc3 = timeit(lambda i: L.attn_prefill_tc3(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, ST()), 1)
-        diff3 = (o.float() - o_tc.float()).abs().max().item()
         ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * H, hd, P(K), P(V), nh * cap * hd, cap * hd, hd, 0, P(o), H, P(cu), P(past), B, nh, hd, Lq, 1, sc, ST()), 1)
         diff = (o.float() - o_tc.float()).abs().max().item()
         q4 = qkv[:, :H].view(B, Lq, nh, hd).transpose(1, 2)
@@ -125,8 +123,7 @@ def bench_attn_prefill(out):
                      "frac_of_sustained_bf16": flop / ms_tc / 1e9 / pk["bf16_tflops_sustained"], "mma_us": ms_mma * 1e3,
                      "mma_TFLOPs": flop / ms_mma / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "torch_sdpa_TFLOPs": flop / ms_sdpa / 1e9,
                      "tc_vs_mma_maxdiff": diff, "tc2_us": ms_tc2 * 1e3, "tc2_TFLOPs": flop / ms_tc2 / 1e9,
-                     "tc2_frac_of_sustained_bf16": flop / ms_tc2 / 1e9 / pk["bf16_tflops_sustained"], "tc2_vs_tc_maxdiff": diff2, "tc3_us": ms_tc3 * 1e3, "tc3_TFLOPs": flop / ms_tc3 / 1e9,
-                     "tc3_frac_of_sustained_bf16": flop / ms_tc3 / 1e9 / pk["bf16_tflops_sustained"], "tc3_vs_tc_maxdiff": diff3})
+                     "tc2_frac_of_sustained_bf16": flop / ms_tc2 / 1e9 / pk["bf16_tflops_sustained"], "tc2_vs_tc_maxdiff": diff2})
         print("ATTN_PREFILL", rows[-1], flush=True)
     out["attn_prefill"] = rows
 
