@@ -125,3 +125,38 @@ def test_synthetic_inputs_are_deterministic():
     assert torch.equal(a, b) and torch.equal(pa, pb) and (a[:, 5] == -200).all() and (a[:, 0] == 1).all()
     d = forced_text_decisions(11, 2, keep_rate=[0.3, 0.7], seed=3)
     assert d.shape == (11, 2) and d.dtype == torch.bool
+
+
+def test_load_pretrained_model_roundtrip(tmp_path):
+    """reference signature + return tuple (llava/model/dynamic_llava_builder.py:35-45, :249) on a synthetic HF-format dir"""
+    import json
+    from safetensors.torch import save_file
+    from llava.model.dynamic_llava_builder import load_pretrained_model
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = {k: v.to(torch.bfloat16).contiguous() for k, v in numpy_state_dict(cfg, 0).items()}
+    tower = tmp_path / "clip"
+    tower.mkdir()
+    json.dump(dict(cfg["vision"]), open(tower / "config.json", "w"))
+    clip_sd = {k[len("model.vision_tower.vision_tower."):]: v for k, v in sd.items() if "vision_tower" in k}
+    save_file(clip_sd, str(tower / "model.safetensors"))
+    ck = tmp_path / "dynamic-llava-toy"
+    ck.mkdir()
+    llm_sd = {k: v for k, v in sd.items() if "vision_tower" not in k}
+    half = len(llm_sd) // 2
+    items = list(llm_sd.items())
+    save_file(dict(items[:half]), str(ck / "model-00001-of-00002.safetensors"))
+    save_file(dict(items[half:]), str(ck / "model-00002-of-00002.safetensors"))
+    cj = {k: v for k, v in cfg.items() if k != "vision"}
+    cj.update(mm_vision_tower=str(tower), mm_projector_type="mlp2x_gelu", model_type="dynamic_llava_llama")
+    json.dump(cj, open(ck / "config.json", "w"))
+    with pytest.warns(UserWarning, match="tokenizer"):
+        tok, model, proc, ctx = load_pretrained_model(str(ck), None, "dynamic-llava-toy", device="cpu")
+    assert tok is None and ctx == 2048 and proc is not None
+    got = model.state_dict()
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    assert model.config.sparse_config["sparse_layer"] == 2 and model.get_vision_tower().is_loaded
+    with pytest.raises(NotImplementedError):
+        load_pretrained_model(str(ck), None, "dynamic-llava-toy", load_4bit=True)
+    with pytest.raises(NotImplementedError):
+        load_pretrained_model(str(ck), "base", "dynamic-llava-lora")
