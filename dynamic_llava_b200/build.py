@@ -26,6 +26,7 @@ SOURCES = [
     "attn_prefill_tc.cu",
     "attn_prefill_tc2.cu",
     "skinny_gemm.cu",
+    "gemm_tc.cu",
     "decode_fused.cu",
     "predictor_ops.cu",
 ]

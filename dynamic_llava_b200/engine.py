@@ -90,6 +90,7 @@ class Engine:
         self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc2")  # "tc2" | "tc" (tcgen05 kernels) | "mma" (warp-MMA tile path)
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
+        self.attn_prefetch_wo = os.environ.get("DLB200_ATTN_PREFETCH_WO", "0") == "1"  # o_proj weight -> L2 during decode attention (measured: no gain)
         self.launches = 0  # kernels of OURS launched (eager path; graph replays counted via launches_per_step)
         self.launches_per_step = 0
 
@@ -221,7 +222,9 @@ class Engine:
         NP = G * G
         cols = torch.empty(B * NP, pk["Kpad"], device=self.device, dtype=self.dtype)
         self.L.im2col_patches(_p(x), _p(cols), B, Cin, S, ps, pk["Kpad"], _stream())
-        pe = F.linear(cols, pk["patch_w"])  # conv-as-GEMM [B*NP, Kpad] x [Kpad, C]
+        pe = torch.empty(B * NP, C, device=self.device, dtype=self.dtype)
+        self.L.gemm_bias_act(_p(cols), _p(pk["patch_w"]), None, _p(pe), B * NP, C, pk["Kpad"], 0, _stream())  # conv as a tcgen05 GEMM tile kernel
+        self.launches += 1
         tok = torch.empty(B * (NP + 1), C, device=self.device, dtype=self.dtype)
         self.L.clip_assemble(_p(pe), _p(vm.embeddings.class_embedding), _p(vm.embeddings.position_embedding.weight), _p(tok), B, NP, C, _stream())
         self.launches += 2
@@ -253,6 +256,14 @@ class Engine:
         B, N, C = f.shape
         f = f.reshape(B * N, C).to(self.dtype)
         p = m.mm_projector
+        H = p[0].weight.shape[0]
+        if C % 64 == 0 and H % 64 == 0:  # mlp2x_gelu on the tcgen05 tile GEMM, bias + GELU fused into the TMEM epilogue
+            y = torch.empty(B * N, H, device=self.device, dtype=self.dtype)
+            self.L.gemm_bias_act(_p(f.contiguous()), _p(p[0].weight), _p(p[0].bias), _p(y), B * N, H, C, 1, _stream())
+            z = torch.empty(B * N, H, device=self.device, dtype=self.dtype)
+            self.L.gemm_bias_act(_p(y), _p(p[2].weight), _p(p[2].bias), _p(z), B * N, H, H, 0, _stream())
+            self.launches += 2
+            return z.view(B, N, -1)
         y = self.act_(F.linear(f, p[0].weight, p[0].bias), 1)
         y = F.linear(y, p[2].weight, p[2].bias)
         return y.view(B, N, -1)
@@ -490,7 +501,8 @@ class Engine:
                 sess.attn_ws = torch.empty(L_.attn_decode_workspace_bytes(B, nh, 16) // 4, device=self.device, dtype=torch.float32)
             L_.attn_decode_fused(_p(sess.partial), s, _p(a.pos), _p(keep if l >= SL else None), _p(pk["cos"]), _p(pk["sin"]), _p(K_), _p(V_),
                                  _p(kvl), _p(sess.attn), _p(sess.attn_ws), B, nh, hd, cap, ns, scale,
-                                 1 if (quirk and l >= SL and keep is not None) else 0, st)
+                                 1 if (quirk and l >= SL and keep is not None) else 0,
+                                 _p(W["wo"]) if self.attn_prefetch_wo else None, W["wo"].numel() * 2, st)
             s = self._gemm(sess, sess.attn, W["wo"], B, H, H)
             L_.dec_reduce_residual_norm(_p(sess.partial), _p(sess.xres), _p(W["ln2"]), _p(sess.xn), B, H, s, eps, st)
             L_.skinny_gemm_swiglu(_p(sess.xn), _p(W["wgu"]), _p(sess.act), B, I, H, st)  # gate|up GEMM with SwiGLU in the epilogue

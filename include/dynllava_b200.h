@@ -56,6 +56,11 @@ int dl_clip_assemble(const void* patch_embed, const void* cls, const void* pos, 
 /* multimodal_encoder/clip_encoder.py:43-51 (select_feature == "patch") */
 int dl_drop_cls(const void* x, void* out, int B, int NP, int C, cudaStream_t stream);
 
+/* K6: dense bf16 GEMM on TMA + tcgen05 tiles, out[M,N] = act(X[M,K] . W[N,K]^T + bias) (act 0 none, 1 GELU-erf on the bf16
+ * rounded sum; bias may be NULL).  Conv2d patch embedding as an im2col GEMM (HF CLIPVisionEmbeddings) and the mlp2x_gelu
+ * projector (multimodal_projector/builder.py:172-179).  K % 64 == 0, N % 8 == 0. */
+int dl_gemm_bias_act(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int act, cudaStream_t stream);
+
 /* ---- K1: predictor score + top-k + gather/compact + index map + CSR header, DML:1867, :1897-1994 ------------- */
 /* logits [B,n_img,2]; forced_keep int64 [B,k] or NULL; hidden_in [B,P,H]; hidden_out [B,P',H], P' = P-n_img+k;
  * keep_index int64 [B,k] ascending; pos_out int32 [B,P'] original positions; cu_seqlens int32 [B+1].
@@ -102,7 +107,9 @@ int dl_attn_decode(const void* q, int q_row_stride, const void* k_arena, const v
  * reduce + bf16 rounding + RoPE + conditional append per (sample, head) inside the attention CTA (DML:1011-1083). */
 int dl_attn_decode_fused(const float* qkv_partial, int n_slices, const int32_t* pos, const uint8_t* keep, const void* cos_table,
                          const void* sin_table, void* k_arena, void* v_arena, const int32_t* kv_len, void* out, void* workspace,
-                         int B, int heads, int head_dim, int cap, int n_split, float scale, int quirk_pad, cudaStream_t stream);
+                         int B, int heads, int head_dim, int cap, int n_split, float scale, int quirk_pad, const void* l2_prefetch,
+                         int64_t l2_prefetch_bytes, cudaStream_t stream);
+/* l2_prefetch (or NULL): device range (the next GEMM's weight) the CTAs ask the TMA unit to pull into L2 while they run. */
 
 /* ---- K2/K6/K7: variable-length attention (warp-MMA tile path), DML:1114-1122; CTL:164-169; HF CLIPAttention ---- */
 /* Addresses: Q(b,i,h) = q + (cu_q[b]+i)*q_tok_stride + h*q_head_stride;

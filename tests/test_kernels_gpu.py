@@ -387,7 +387,9 @@ def test_attn_decode_fused_equals_unfused(L, lens, n_split, S, quirk):
     L.attn_decode(P(q), H, P(K1), P(V1), P(ks), P(vs), P(kvl), P(o1), P(ws), B, nh, hd, cap, n_split, sc, quirk, ST())
     K2, V2 = K.to(DEV).clone(), V.to(DEV).clone()
     o2 = torch.empty(B, H, device=DEV, dtype=BF)
-    L.attn_decode_fused(P(part), S, P(pos), P(keep), P(cos), P(sin), P(K2), P(V2), P(kvl), P(o2), P(ws), B, nh, hd, cap, n_split, sc, quirk, ST())
+    pf = torch.zeros(1 << 20, device=DEV, dtype=torch.uint8)
+    L.attn_decode_fused(P(part), S, P(pos), P(keep), P(cos), P(sin), P(K2), P(V2), P(kvl), P(o2), P(ws), B, nh, hd, cap, n_split, sc, quirk,
+                        P(pf) if S > 1 else None, pf.numel(), ST())
     torch.cuda.synchronize()
     assert torch.equal(K1, K2) and torch.equal(V1, V2)
     assert torch.equal(o1, o2), (o1.float() - o2.float()).abs().max()
@@ -542,6 +544,23 @@ def test_skinny_gemm_swiglu_epilogue(L, M, I, K):
     gu = (x.float() @ w.float().T)
     want = (F.silu(gu[:, :I].to(BF)) * gu[:, I:].to(BF)).float()
     assert (act.float().cpu() - want).abs().max() < 2e-2 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K,act,bias", [(4608, 1024, 640, 0, False), (32, 128, 640, 0, False), (4608, 4096, 1024, 1, True), (1152, 256, 128, 1, True),
+                                            (300, 1000, 192, 0, True)])
+def test_gemm_tcgen05_bias_act(L, M, N, K, act, bias):
+    x, w = rnd(M, K, seed=150), rnd(N, K, seed=151, scale=0.05)
+    b = rnd(N, seed=152, scale=0.1) if bias else None
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=BF)
+    L.gemm_bias_act(P(x), P(w), P(b), P(out), M, N, K, act, ST())
+    torch.cuda.synchronize()
+    y = x.float() @ w.float().T
+    if bias:
+        y = y + b.float()
+    ref = F.gelu(y.to(BF)).float() if act == 1 else y
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max() < 1.5e-2 * max(1.0, ref.abs().max().item())
 
 
 def test_skinny_gemm_split_heuristic(L):

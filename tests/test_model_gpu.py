@@ -229,3 +229,33 @@ def test_clip_and_projector_match_oracle():
     assert (got - ref32).abs().max() <= 2 * floor + 1e-2 * ref32.abs().max()
     f = model.get_vision_tower()(pix.cuda())
     assert f.shape == (2, 16, 128) and f.dtype == pix.dtype
+
+
+def test_ragged_kv_stress_per_sample_rates():
+    """BASELINE config 3 in miniature: per-sample DIFFERENT forced keep rates so the per-sample KV lengths diverge over a longer
+    decode (CUDA-graph replayed); bookkeeping must equal DynamicCachePlus.true_cache_length sample by sample."""
+    from dynamic_llava_b200.synthetic import forced_text_decisions
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b3_nodrop", out_pred=True)
+    n_new = 24
+    fd = forced_text_decisions(n_new - 1, g["B"], keep_rate=[0.1, 0.5, 0.9], seed=7)
+    rec = {}
+    O.model_forward(sd16, cfg, ids, images=pix, record=rec)
+    keep = rec["keep_index"]
+    out = model.generate(ids, images=pix, max_new_tokens=n_new, do_sample=False, eos_token_id=None, forced_keep_index=keep,
+                         forced_text_decisions=fd).cpu()
+    ref = O.greedy_loop(sd16, cfg, ids, pix, n_new, forced_keep_index=keep, forced_text_decisions=fd, per_sample=True)
+    ref32 = O.greedy_loop(sd32, cfg, ids, pix.float(), n_new, forced_keep_index=keep, forced_text_decisions=fd, per_sample=True,
+                          teacher_tokens=ref["tokens"])
+    lens = next(iter(model._sessions.values())).arena.kv_len.cpu().long()
+    assert torch.equal(lens, ref["true_len"])
+    P = g["T"] - 1 + 16
+    assert lens[0].tolist() == [P + n_new - 1] * 3 and lens[-1].tolist() == (P - 8 + fd.sum(0)).tolist()
+    assert len(set(lens[-1].tolist())) == 3  # genuinely ragged
+    floor = (ref["logits"] - ref32["logits"]).abs().max().item()
+    top2 = ref["logits"].topk(2, dim=-1).values
+    sure = ((top2[..., 0] - top2[..., 1]) > 4 * floor).T
+    for b in range(g["B"]):
+        n = 0
+        while n < n_new and bool(sure[b, n]):
+            n += 1
+        assert out[b, :n].tolist() == ref["tokens"][b, :n].tolist(), (b, n)

@@ -186,6 +186,24 @@ def bench_skinny(out):
     out["skinny_gemm"] = rows
 
 
+def bench_gemm(out):
+    import torch.nn.functional as F
+    pk = peaks()
+    rows = []
+    for name, M, N, K in [("clip patch-embed B=8", 4608, 1024, 640), ("projector fc1 B=8", 4608, 4096, 1024), ("clip fc1 B=8", 4616, 4096, 1024),
+                          ("llama qkv prefill B=8", 4856, 12288, 4096)]:
+        x, w, b = torch.randn(M, K, device=DEV, dtype=BF), torch.randn(N, K, device=DEV, dtype=BF) * 0.05, torch.randn(N, device=DEV, dtype=BF)
+        o = torch.empty(M, N, device=DEV, dtype=BF)
+        ms = timeit(lambda i: L.gemm_bias_act(P(x), P(w), P(b), P(o), M, N, K, 0, ST()), 1)
+        ms_c = timeit(lambda i: F.linear(x, w, b), 1)
+        fl = 2.0 * M * N * K
+        rows.append({"case": name, "GFLOP": fl / 1e9, "tcgen05_tile_us": ms * 1e3, "tcgen05_tile_TFLOPs": fl / ms / 1e9,
+                     "frac_of_sustained_bf16": fl / ms / 1e9 / pk["bf16_tflops_sustained"], "cublaslt_us": ms_c * 1e3, "cublaslt_TFLOPs": fl / ms_c / 1e9,
+                     "maxdiff_vs_cublas": (o.float() - F.linear(x, w, b).float()).abs().max().item()})
+        print("GEMM", rows[-1], flush=True)
+    out["gemm_tc"] = rows
+
+
 def main():
     global L
     ap = argparse.ArgumentParser()
@@ -203,6 +221,8 @@ def main():
         bench_attn_decode(out)
     if "skinny" in todo:
         bench_skinny(out)
+    if "gemm" in todo:
+        bench_gemm(out)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
 
