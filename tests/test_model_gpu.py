@@ -259,3 +259,58 @@ def test_ragged_kv_stress_per_sample_rates():
         while n < n_new and bool(sure[b, n]):
             n += 1
         assert out[b, :n].tolist() == ref["tokens"][b, :n].tolist(), (b, n)
+
+
+@pytest.mark.parametrize("rate,k", [(1.0, 16), (0.0, 0), (0.07, 1)])
+def test_vision_keep_rate_extremes(rate, k):
+    """k = int(n_img * rate) (dynamic_modeling_llama.py:1899-1901): keep everything, keep nothing, keep one."""
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b1_natural", out_pred=False)
+    cfg["sparse_config"]["vision_keep_rate"] = rate
+    model.config.sparse_config["vision_keep_rate"] = rate
+    rec16 = {}
+    ref16, past_ref = O.model_forward(sd16, cfg, ids, images=pix, record=rec16)
+    ref32, _ = O.model_forward(sd32, cfg, ids, images=pix.float(), forced_keep_index=rec16["keep_index"])
+    rec = {}
+    out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=rec16["keep_index"], record=rec)
+    P = g["T"] - 1 + 16
+    assert rec["keep_index"].shape == (1, k) and out.logits.shape[1] == P - 16 + k
+    floor = (ref16 - ref32).abs().max().item()
+    assert (out.logits.cpu() - ref32).abs().max() <= 2 * floor + 1e-2 * ref32.abs().max()
+    assert [int(x[0]) for x in out.past_key_values[1]] == [int(x[0]) for x in past_ref[1]]
+
+
+def test_forward_loop_grows_cache_beyond_initial_room():
+    """the hand-rolled loop of the reference (model_lvis_for_meteor.py:145-174) has no max length: the arena must re-slab
+    transparently when a caller decodes past the room reserved at prefill, without changing results."""
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b1_natural", out_pred=False)
+    n = 70  # > the 64 slots reserved by forward()
+    out = model(ids.cuda(), images=pix.cuda())
+    past, cur = out.past_key_values, out.logits[:, -1].argmax(-1).reshape(1, 1)
+    toks = [int(cur)]
+    for _ in range(n):
+        out = model(cur, past_key_values=past)
+        past, cur = out.past_key_values, out.logits[:, -1].argmax(-1).reshape(1, 1)
+        toks.append(int(cur))
+    P = g["T"] - 1 + 16
+    assert past[0][0][0].shape[2] == P + n and past[0][-1][0].shape[2] == P - 8 + n
+    gen = model.generate(ids, images=pix, max_new_tokens=n + 1, do_sample=False, eos_token_id=None).cpu()[0].tolist()
+    agree = sum(int(a == b) for a, b in zip(toks, gen))
+    assert toks[:8] == gen[:8] and agree >= 0.6 * len(gen)  # same math; later steps may fork at near-tie logits
+
+
+def test_generate_eos_stops_early_and_text_only_generate():
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b1_natural", out_pred=False)
+    full = model.generate(ids, images=pix, max_new_tokens=40, do_sample=False, eos_token_id=None).cpu()
+    eos = int(full[0, 3])
+    short = model.generate(ids, images=pix, max_new_tokens=40, do_sample=False, eos_token_id=eos).cpu()
+    assert short.shape[1] == 4 and short[0].tolist() == full[0, :4].tolist()
+    txt = ids.clone()
+    txt[txt == -200] = 9
+    t = model.generate(txt, max_new_tokens=5, do_sample=False, eos_token_id=None).cpu()
+    ref = O.greedy_loop  # text-only oracle: no images -> dense prefill, predictor decisions still apply at decode
+    lg, past = O.llama_forward(sd16, cfg, input_ids=txt)
+    assert t.shape == (1, 5) and int(t[0, 0]) == int(lg[0, -1].argmax())
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, images=pix, do_sample=True, max_new_tokens=2)
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, images=pix, num_beams=2, max_new_tokens=2)
