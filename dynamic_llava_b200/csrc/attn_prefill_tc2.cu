@@ -21,13 +21,16 @@
 #include "../../include/dynllava_b200.h"
 
 #define T2_THREADS 320
-#define T2_TILE_BYTES (128 * 128 * 2)
 #define T2_RESCALE_LOG2 8.0f
 
+// HD = 128: Llama prefill (causal, K/V in the arena).  HD = 64: CLIP ViT-L/14 and the VisionPredictor blocks (non-causal,
+// q|k|v packed in one fused projection buffer) — K6/K7's attention on the same TMA + tcgen05 pipeline.
+template <int HD>
 struct T2Smem {
-  alignas(1024) uint8_t q[2][T2_TILE_BYTES];
-  alignas(1024) uint8_t k[2][T2_TILE_BYTES];
-  alignas(1024) uint8_t v[2][T2_TILE_BYTES];
+  static constexpr int TILE = 128 * HD * 2;  // one 128-row operand tile = HD/64 blocks of 16 KB (128B-swizzled)
+  alignas(1024) uint8_t q[2][TILE];
+  alignas(1024) uint8_t k[2][TILE];
+  alignas(1024) uint8_t v[2][TILE];
   alignas(8) uint64_t q_full;
   alignas(8) uint64_t k_full[2];
   alignas(8) uint64_t v_full[2];
@@ -73,12 +76,16 @@ DL_DEVINL float ex2(float x) {
   return y;
 }
 
+template <int HD, bool CAUSAL, bool PACKED>
 __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
     const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
     const __grid_constant__ CUtensorMap tmap_v, bf16* __restrict__ out, int64_t o_tok_stride,
     const int32_t* __restrict__ cu_q, const int32_t* __restrict__ kv_past, int heads, int cap, float scale_log2) {
+  constexpr int T2_TILE_BYTES = T2Smem<HD>::TILE;
+  constexpr int NBOX = HD / 64;   // 64-column TMA boxes per operand tile
+  constexpr int KSTEPS = HD / 16;  // K = 16 MMAs of S = Q K^T
   extern __shared__ uint8_t smem_raw[];
-  T2Smem& S = *reinterpret_cast<T2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  T2Smem<HD>& S = *reinterpret_cast<T2Smem<HD>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // causal: the last query tiles see the most keys -> schedule them first (longest-processing-time order)
   const int mt = gridDim.x - 1 - blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -90,10 +97,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
   const int kv_total = past + q_len;
   const int off = past;
   const bool b_active = (m0 + 128) < q_len;
-  const int n_a = (min(kv_total, m0 + 128 + off) + 127) / 128;
-  const int n_b = b_active ? (min(kv_total, m0 + 256 + off) + 127) / 128 : 0;
+  const int n_a = ((CAUSAL ? min(kv_total, m0 + 128 + off) : kv_total) + 127) / 128;
+  const int n_b = b_active ? ((CAUSAL ? min(kv_total, m0 + 256 + off) : kv_total) + 127) / 128 : 0;
   const int n_tiles = max(n_a, n_b);
-  const int kv_row0 = (b * heads + h) * cap;
+  // K/V rows: arena slab of (sample, head), or — PACKED — the sample's own token rows of the fused q|k|v buffer
+  const int kv_row0 = PACKED ? q_start : (b * heads + h) * cap;
+  const int kv_col0 = PACKED ? h * HD : 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -120,37 +129,36 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       mbar_expect_tx(&S.q_full, (b_active ? 2 : 1) * T2_TILE_BYTES);
-      tma_load_2d(S.q[0], &tmap_q, h * 128, q_start + m0, &S.q_full);
-      tma_load_2d(S.q[0] + T2_TILE_BYTES / 2, &tmap_q, h * 128 + 64, q_start + m0, &S.q_full);
-      if (b_active) {
-        tma_load_2d(S.q[1], &tmap_q, h * 128, q_start + m0 + 128, &S.q_full);
-        tma_load_2d(S.q[1] + T2_TILE_BYTES / 2, &tmap_q, h * 128 + 64, q_start + m0 + 128, &S.q_full);
+#pragma unroll
+      for (int x = 0; x < NBOX; ++x) {
+        tma_load_2d(S.q[0] + x * 16384, &tmap_q, h * HD + x * 64, q_start + m0, &S.q_full);
+        if (b_active) tma_load_2d(S.q[1] + x * 16384, &tmap_q, h * HD + x * 64, q_start + m0 + 128, &S.q_full);
       }
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
         mbar_wait(&S.kv_empty[s], ((j >> 1) & 1) ^ 1);
         const int row = kv_row0 + j * 128;
         mbar_expect_tx(&S.k_full[s], T2_TILE_BYTES);
-        tma_load_2d(S.k[s], &tmap_k, 0, row, &S.k_full[s]);
-        tma_load_2d(S.k[s] + T2_TILE_BYTES / 2, &tmap_k, 64, row, &S.k_full[s]);
+#pragma unroll
+        for (int x = 0; x < NBOX; ++x) tma_load_2d(S.k[s] + x * 16384, &tmap_k, kv_col0 + x * 64, row, &S.k_full[s]);
         mbar_expect_tx(&S.v_full[s], T2_TILE_BYTES);
-        tma_load_2d(S.v[s], &tmap_v, 0, row, &S.v_full[s]);
-        tma_load_2d(S.v[s] + T2_TILE_BYTES / 2, &tmap_v, 64, row, &S.v_full[s]);
+#pragma unroll
+        for (int x = 0; x < NBOX; ++x) tma_load_2d(S.v[s] + x * 16384, &tmap_v, kv_col0 + x * 64, row, &S.v_full[s]);
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 0, 1);  // B (= V) MN-major
+      constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, HD, 0, 1);  // N = head_dim; B (= V) MN-major
       auto issue_s = [&](int g, int j) {
         const int s = j & 1;
         mbar_wait(&S.k_full[s], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t qa = smem_u32(S.q[g]), ka = smem_u32(S.k[s]);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t o = (kk >> 2) * (T2_TILE_BYTES / 2) + (kk & 3) * 32;
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          const uint32_t o = (kk >> 2) * 16384 + (kk & 3) * 32;
           umma_bf16_ss(tmem + (uint32_t)g * 128, umma_desc_kmajor_sw128(qa + o), umma_desc_kmajor_sw128(ka + o), IDESC_QK, kk > 0 ? 1u : 0u);
         }
         umma_commit(&S.s_full[g]);
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
         const uint32_t va = smem_u32(S.v[s]);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA = 8 packed P columns and 2 KB of V rows
-          umma_bf16_ts(tmem + 256 + (uint32_t)g * 128, tmem + (uint32_t)g * 128 + kk * 8, t2_desc_mn_sw128(va + kk * 2048, T2_TILE_BYTES / 2),
+          umma_bf16_ts(tmem + 256 + (uint32_t)g * 128, tmem + (uint32_t)g * 128 + kk * 8, t2_desc_mn_sw128(va + kk * 2048, 16384),
                        IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&S.o_done[g]);
       };
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
       const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t ts = tmem + (uint32_t)g * 128 + lane_addr;
       const uint32_t to = tmem + 256 + (uint32_t)g * 128 + lane_addr;
-      const int key_lim = min(kv_total - 1, qi + off);
+      const int key_lim = CAUSAL ? min(kv_total - 1, qi + off) : kv_total - 1;
       float m_ref = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < n_g; ++j) {
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
           mbar_wait(&S.o_done[g], (j - 1) & 1);
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < HD / 32; ++c) {
             uint32_t ov[32];
             tmem_ld_32x32b_x32(to + c * 32, ov);
             tmem_ld_wait();
@@ -260,9 +268,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
       mbar_wait(&S.o_done[g], (n_g - 1) & 1);
       tc_fence_after();
       const float inv = 1.f / l_run;
-      bf16* dst = out + (int64_t)(q_start + qi) * o_tok_stride + (int64_t)h * 128;
+      bf16* dst = out + (int64_t)(q_start + qi) * o_tok_stride + (int64_t)h * HD;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < HD / 32; ++c) {
         uint32_t ov[32];
         tmem_ld_32x32b_x32(to + c * 32, ov);
         tmem_ld_wait();
@@ -283,6 +291,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+template <int HD, bool CAUSAL, bool PACKED>
+static int launch_t2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* out, int64_t o_tok_stride,
+                     const int32_t* cu_q, const int32_t* kv_past, int B, int heads, int cap, int max_q_len, float scale,
+                     cudaStream_t stream) {
+  const int smem = (int)sizeof(T2Smem<HD>) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc2_kernel<HD, CAUSAL, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return dl_set_error((int)e, "dl_attn_tc2(smem attr)");
+    attr_set = true;
+  }
+  dim3 grid((max_q_len + 255) / 256, heads, B);
+  attn_prefill_tc2_kernel<HD, CAUSAL, PACKED><<<grid, T2_THREADS, smem, stream>>>(tq, tk, tv, out, o_tok_stride, cu_q, kv_past, heads, cap,
+                                                                                  scale * 1.4426950408889634f);
+  DL_CHECK_LAUNCH("dl_attn_tc2");
+}
+
 extern "C" int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
                                    int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
                                    int cap, int max_q_len, float scale, cudaStream_t stream) {
@@ -294,15 +319,23 @@ extern "C" int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const vo
   if (rc) return rc;
   rc = dl_make_tmap_2d(&tv, v_arena, (uint64_t)B * heads * cap, 128, 128, 128, 64);
   if (rc) return rc;
-  const int smem = (int)sizeof(T2Smem) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return dl_set_error((int)e, "dl_attn_prefill_tc2(smem attr)");
-    attr_set = true;
-  }
-  dim3 grid((max_q_len + 255) / 256, heads, B);
-  attn_prefill_tc2_kernel<<<grid, T2_THREADS, smem, stream>>>(tq, tk, tv, (bf16*)out, o_tok_stride, cu_q, kv_past, heads, cap,
-                                                              scale * 1.4426950408889634f);
-  DL_CHECK_LAUNCH("dl_attn_prefill_tc2");
+  return launch_t2<128, true, false>(tq, tk, tv, (bf16*)out, o_tok_stride, cu_q, kv_past, B, heads, cap, max_q_len, scale, stream);
+}
+
+// K6/K7: non-causal attention over a fused projection qkv [n_tok, 3*heads*64] = [q | k | v] (HF CLIPAttention;
+// custom_transformer_layer.py:153-180), per-sample token ranges from the CSR header cu_q.  out [n_tok, heads*64].
+extern "C" int dl_attn_packed_tc(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
+                                 int max_q_len, float scale, cudaStream_t stream) {
+  DL_REQUIRE(head_dim == 64, "dl_attn_packed_tc");
+  if (B == 0 || max_q_len == 0) return 0;
+  const int64_t C = (int64_t)heads * 64;
+  const bf16* base = (const bf16*)qkv;
+  alignas(64) CUtensorMap tq, tk, tv;
+  int rc = dl_make_tmap_2d(&tq, base, (uint64_t)n_tok, (uint64_t)C, (uint64_t)(3 * C), 128, 64);
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&tk, base + C, (uint64_t)n_tok, (uint64_t)C, (uint64_t)(3 * C), 128, 64);
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&tv, base + 2 * C, (uint64_t)n_tok, (uint64_t)C, (uint64_t)(3 * C), 128, 64);
+  if (rc) return rc;
+  return launch_t2<64, false, true>(tq, tk, tv, (bf16*)out, C, cu_q, nullptr, B, heads, 0, max_q_len, scale, stream);
 }

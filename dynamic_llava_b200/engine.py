@@ -88,6 +88,7 @@ class Engine:
             raise RuntimeError("kernels compute in bf16: load the model with torch_dtype=torch.bfloat16")
         self.packed = None
         self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc2")  # "tc2" | "tc" (tcgen05 kernels) | "mma" (warp-MMA tile path)
+        self.packed_attn = os.environ.get("DLB200_PACKED_ATTN", "tc")  # CLIP / predictor attention: "tc" (tcgen05) | "mma"
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
         self.attn_prefetch_wo = os.environ.get("DLB200_ATTN_PREFETCH_WO", "0") == "1"  # o_proj weight -> L2 during decode attention (measured: no gain)
@@ -195,6 +196,10 @@ class Engine:
         C = heads * hd
         out = torch.empty(B * N, C, device=qkv.device, dtype=qkv.dtype)
         cu = torch.arange(0, (B + 1) * N, N, device=qkv.device, dtype=torch.int32)
+        if hd == 64 and not causal and self.packed_attn == "tc":
+            self.L.attn_packed_tc(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), _stream())
+            self.launches += 1
+            return out
         es = qkv.element_size()
         k = ctypes.c_void_p(qkv.data_ptr() + C * es)
         v = ctypes.c_void_p(qkv.data_ptr() + 2 * C * es)

@@ -130,6 +130,12 @@ int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena
                         int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
                         int cap, int max_q_len, float scale, cudaStream_t stream);
 
+/* K6/K7 on the same tcgen05 pipeline: non-causal attention, head_dim 64, q|k|v packed in one fused projection buffer
+ * qkv [n_tok, 3*heads*64]; per-sample ranges from cu_q; out [n_tok, heads*64].  HF CLIPAttention (CLIP ViT-L/14) and the
+ * VisionPredictor blocks (CTL:153-180). */
+int dl_attn_packed_tc(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
+                      int max_q_len, float scale, cudaStream_t stream);
+
 /* ---- decode-step weight streaming: every nn.Linear at q_len == 1 (DML:1011-1013, :1127, :328, :2709) ----------- */
 /* partial fp32 [splits, M, N] = per-split X[M,K] . W[N,K]^T; M <= 64, K % 64 == 0.  TMA + tcgen05.
  * l2_prefetch_mb: bytes of W (total over the grid) each launch asks the TMA unit to pull into L2 ahead of its smem ring

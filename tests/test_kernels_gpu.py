@@ -473,6 +473,25 @@ def test_attn_varlen_packed_qkv(L):
             assert (out[sl, h * hd:(h + 1) * hd].float().cpu() - ref).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("B,N,nh", [(2, 577, 16), (3, 576, 8), (2, 17, 2), (1, 300, 4)])
+def test_attn_packed_tcgen05_noncausal_hd64(L, B, N, nh):
+    """CLIP (577 tokens, 16 heads) and predictor (576 tokens, 8 heads) attention on the tcgen05 pipeline vs fp32 attention."""
+    hd = 64
+    C = nh * hd
+    qkv = rnd(B * N, 3 * C, seed=91)
+    out = torch.full((B * N, C), float("nan"), device=DEV, dtype=BF)
+    cu = torch.arange(0, (B + 1) * N, N, dtype=torch.int32, device=DEV)
+    L.attn_packed_tc(P(qkv), P(out), P(cu), B * N, B, nh, hd, N, 1.0 / math.sqrt(hd), ST())
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    for b in range(B):
+        for h in range(nh):
+            sl = slice(b * N, (b + 1) * N)
+            ref = _sdpa_ref(qkv[sl, h * hd:(h + 1) * hd], qkv[sl, C + h * hd:C + (h + 1) * hd], qkv[sl, 2 * C + h * hd:2 * C + (h + 1) * hd])
+            assert (got[sl, h * hd:(h + 1) * hd] - ref).abs().max() < 2e-2, (b, h)
+
+
 @pytest.mark.parametrize("q_lens,pasts", [([128], [0]), ([146, 146], [0, 0]), ([607, 33, 128, 300], [0, 0, 0, 0]), ([19, 70], [27, 5]),
                                           ([1587], [0])])
 def test_attn_prefill_tcgen05(L, q_lens, pasts):

@@ -126,6 +126,25 @@ def bench_attn_prefill(out):
                      "tc2_frac_of_sustained_bf16": flop / ms_tc2 / 1e9 / pk["bf16_tflops_sustained"], "tc2_vs_tc_maxdiff": diff2})
         print("ATTN_PREFILL", rows[-1], flush=True)
     out["attn_prefill"] = rows
+    rows = []
+    for name, B, nh, N in [("CLIP B=8 577x16h", 8, 16, 577), ("predictor B=8 576x8h", 8, 8, 576)]:
+        hd, C = 64, nh * 64
+        qkv = torch.randn(B * N, 3 * C, device=DEV, dtype=BF)
+        o = torch.empty(B * N, C, device=DEV, dtype=BF)
+        cu = torch.arange(0, (B + 1) * N, N, device=DEV, dtype=torch.int32)
+        flop = 4.0 * N * N * C * B
+        sc = 1.0 / math.sqrt(hd)
+        ms_tc = timeit(lambda i: L.attn_packed_tc(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, ST()), 1)
+        o1 = o.clone()
+        kp = ctypes.c_void_p(qkv.data_ptr() + C * 2)
+        vp = ctypes.c_void_p(qkv.data_ptr() + 2 * C * 2)
+        ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * C, hd, kp, vp, 0, hd, 3 * C, 1, P(o), C, P(cu), None, B, nh, hd, N, 0, sc, ST()), 1)
+        q4 = qkv.view(B, N, 3, nh, hd).permute(2, 0, 3, 1, 4)
+        ms_sdpa = timeit(lambda i: F.scaled_dot_product_attention(q4[0], q4[1], q4[2]), 1)
+        rows.append({"case": name, "GFLOP": flop / 1e9, "tcgen05_us": ms_tc * 1e3, "tcgen05_TFLOPs": flop / ms_tc / 1e9, "mma_us": ms_mma * 1e3,
+                     "mma_TFLOPs": flop / ms_mma / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "maxdiff_tc_vs_mma": (o.float() - o1.float()).abs().max().item()})
+        print("ATTN_PACKED", rows[-1], flush=True)
+    out["attn_packed_hd64"] = rows
 
 
 def bench_attn_decode(out):
