@@ -160,3 +160,54 @@ def test_load_pretrained_model_roundtrip(tmp_path):
         load_pretrained_model(str(ck), None, "dynamic-llava-toy", load_4bit=True)
     with pytest.raises(NotImplementedError):
         load_pretrained_model(str(ck), "base", "dynamic-llava-lora")
+
+
+class _ToyTok:
+    """whitespace tokenizer that prepends BOS like Llama's sentencepiece tokenizer does"""
+    bos_token_id = 1
+
+    def __call__(self, text):
+        class R:
+            pass
+        r = R()
+        r.input_ids = [1] + [3 + (sum(map(ord, w)) % 500) for w in text.split()]
+        return r
+
+
+def test_host_prompt_and_image_prep():
+    """the eval drivers' host prep (llava/dynamic_eval/model_vqa_loader.py:60-80): conv template -> tokenizer_image_token -> process_images"""
+    from PIL import Image
+    from transformers import CLIPImageProcessor
+    from llava.conversation import conv_templates
+    from llava.constants import DEFAULT_IMAGE_TOKEN, IMAGE_TOKEN_INDEX
+    from llava.mm_utils import expand2square, get_model_name_from_path, process_images, tokenizer_image_token
+    conv = conv_templates["vicuna_v1"].copy()
+    conv.append_message(conv.roles[0], DEFAULT_IMAGE_TOKEN + "\nWhat is shown?")
+    conv.append_message(conv.roles[1], None)
+    prompt = conv.get_prompt()
+    assert prompt.endswith("USER: <image>\nWhat is shown? ASSISTANT:") and prompt.startswith("A chat between")
+    assert conv_templates["vicuna_v1"].messages == []  # copy() does not leak turns into the template
+    conv.messages[-1][1] = "A cat."
+    assert conv.get_prompt().endswith("ASSISTANT: A cat.</s>")
+    ids = tokenizer_image_token(prompt, _ToyTok(), IMAGE_TOKEN_INDEX, return_tensors="pt")
+    assert ids.dtype == torch.long and ids[0] == 1 and (ids == 1).sum() == 1 and (ids == IMAGE_TOKEN_INDEX).sum() == 1
+    left, right = prompt.split(DEFAULT_IMAGE_TOKEN)
+    assert int((ids == IMAGE_TOKEN_INDEX).nonzero()[0]) == len(left.split()) + 1
+    assert len(ids) == 1 + len(left.split()) + 1 + len(right.split())
+    assert tokenizer_image_token("a <image> b <image> c", _ToyTok()).count(IMAGE_TOKEN_INDEX) == 2
+    assert get_model_name_from_path("/x/dynamic-llava-7b/checkpoint-100/") == "dynamic-llava-7b_checkpoint-100"
+    assert get_model_name_from_path("results/dynamic-llava-7b") == "dynamic-llava-7b"
+    proc = CLIPImageProcessor(size={"shortest_edge": 56}, crop_size={"height": 56, "width": 56})
+    img = Image.new("RGB", (80, 40), (255, 0, 0))
+    sq = expand2square(img, (0, 0, 255))
+    assert sq.size == (80, 80) and sq.getpixel((0, 0)) == (0, 0, 255) and sq.getpixel((40, 40)) == (255, 0, 0)
+
+    class Cfg:
+        image_aspect_ratio = "pad"
+    px = process_images([img, img], proc, Cfg())
+    assert px.shape == (2, 3, 56, 56)
+    Cfg.image_aspect_ratio = None
+    assert process_images([img], proc, Cfg()).shape == (1, 3, 56, 56)
+    Cfg.image_aspect_ratio = "anyres"
+    with pytest.raises(NotImplementedError):
+        process_images([img], proc, Cfg())
