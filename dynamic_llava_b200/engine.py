@@ -450,6 +450,33 @@ class Engine:
         xn = self.rmsnorm(last, m.norm.weight, c.rms_norm_eps)
         return F.linear(xn, self.model.lm_head.weight, out=None)
 
+    @torch.no_grad()
+    def continue_prefill(self, sess: Session, input_ids):
+        """q_len > 1 over an existing cache (a new user turn): DynamicLlamaModel.forward with a past and
+        `use_instruct_predictor=False` (dynamic_modeling_llama.py:1714-1722 positions from the layer-0 length, per-layer causal
+        mask offset by that layer's cached length :1791-1818, plain append in every layer :1078-1083).  Per-sample cache
+        lengths may differ (earlier dropped tokens); each sample's new keys land right after ITS cached keys."""
+        self._check_packed()
+        c = self.cfg
+        m = self.model.model
+        a = sess.arena
+        B, Tq = input_ids.shape
+        H = c.hidden_size
+        ids = input_ids.to(self.device, torch.int64).contiguous()
+        x = torch.empty(B * Tq, H, device=self.device, dtype=self.dtype)
+        self.L.embed_rows(_p(ids), _p(m.embed_tokens.weight), _p(x), B * Tq, H, _stream())
+        self.launches += 1
+        pos = (a.pos.view(B, 1) + torch.arange(Tq, device=self.device, dtype=torch.int32).view(1, Tq)).reshape(-1).contiguous()
+        cu = torch.arange(0, (B + 1) * Tq, Tq, device=self.device, dtype=torch.int32)
+        for l in range(c.num_hidden_layers):
+            x = self._prefill_layer(l, x, pos, cu, sess, B, Tq)
+        self.L.kv_advance(_p(a.kv_len), _p(a.pos), None, None, c.num_hidden_layers, B, c.sparse_config["sparse_layer"], Tq, Tq, _stream())
+        self.launches += 1
+        a.host_len_lo += Tq
+        a.host_ub_hi += Tq
+        xn = self.rmsnorm(x, m.norm.weight, c.rms_norm_eps)
+        return F.linear(xn, self.model.lm_head.weight).view(B, Tq, -1)
+
     # ------------------------------------------------------------------------------------------------------------
     # decode step (q_len == 1): weight streaming + ragged attention, no host sync, CUDA-graph replayable
     # ------------------------------------------------------------------------------------------------------------

@@ -261,13 +261,21 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         if not isinstance(past_key_values, LegacyPastView):
             raise NotImplementedError("past_key_values must be the object returned by a previous forward() of this model")
         ids = input_ids if input_ids is not None else None
-        if ids is None or ids.shape[1] != 1:
-            raise NotImplementedError("multi-token continuation with a KV cache (new-instruction turn) is a SURVEY.md §8f 'next' row")
+        if ids is None:
+            raise NotImplementedError("continuing a cache needs input_ids (inputs_embeds continuation is not a reference flow)")
         sess = past_key_values.session
         a = sess.arena
-        if a.room() < 1:
-            a.grow(a.cap_lo + 1, a.cap_hi + 1)
+        n_in = ids.shape[1]
+        if a.room() < n_in:
+            a.grow(a.host_len_lo + n_in + 64, a.host_ub_hi + n_in + 64)
             sess.graph = None
+        if n_in > 1:
+            # a new user turn over the existing cache (model_lvis_multi_round_for_meteor.py:150-185)
+            if sc["use_text_predictor"] and sc["use_instruct_predictor"]:
+                raise NotImplementedError("instruct predictor on a new turn (dynamic_modeling_llama.py:2506-2521) is a SURVEY.md §8f "
+                                          "'next' row; the reference's scripts run with use_instruct_predictor=False (README.md:110)")
+            logits = eng.continue_prefill(sess, ids)
+            return CausalLMOutputWithPast(logits=logits.float(), past_key_values=LegacyPastView(a, sess))
         sess.next_ids.copy_(ids.reshape(-1).to(self.device, torch.int64))
         use_dec = bool(sc["use_text_predictor"] and sc["use_output_text_predictor"])
         if forced_text_decision is not None:

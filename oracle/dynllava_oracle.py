@@ -212,7 +212,18 @@ def _attention(sd: StateDict, cfg: dict, i: int, x: Tensor, position_ids: Tensor
         cache.update(k, v, i, text_decision)
     else:  # :1078-1083
         k_all, v_all = cache.update(k, v, i)
-    o = F.scaled_dot_product_attention(q, k_all, v_all, attn_mask=None, dropout_p=0.0, is_causal=Lq > 1)  # :1114-1122
+    past_i = k_all.shape[-2] - Lq
+    if Lq > 1 and past_i > 0:
+        # multi-token continuation over a cache (new user turn): the per-layer mask helper (:1805-1810, transformers
+        # `_prepare_4d_causal_attention_mask_for_sdpa` with attention_mask=None, q_len > 1, kv > q) materialises a causal
+        # 4-D additive mask offset by the cached length, and SDPA runs with is_causal=False (:1121)
+        m = torch.full((Lq, Lq), torch.finfo(q.dtype).min, dtype=q.dtype)
+        c = torch.arange(Lq)
+        m.masked_fill_(c < (c + 1).view(Lq, 1), 0)
+        m = torch.cat([torch.zeros(Lq, past_i, dtype=q.dtype), m], dim=-1)[None, None].expand(B, 1, Lq, past_i + Lq)
+        o = F.scaled_dot_product_attention(q, k_all, v_all, attn_mask=m, dropout_p=0.0, is_causal=False)
+    else:
+        o = F.scaled_dot_product_attention(q, k_all, v_all, attn_mask=None, dropout_p=0.0, is_causal=Lq > 1)  # :1114-1122
     o = o.transpose(1, 2).contiguous().reshape(B, Lq, H)
     return F.linear(o, sd[p + "o_proj.weight"])
 

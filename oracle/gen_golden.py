@@ -180,5 +180,39 @@ def main():
                   "true_len", res["true_len_hist"][-1].tolist())
 
 
+@torch.no_grad()
+def multiround_case(out_dir, scratch):
+    """second user turn: q_len > 1 over an existing ragged cache (llava/dynamic_eval/model_lvis_multi_round_for_meteor.py:150-185
+    with use_instruct_predictor=False, README.md:110): prefill -> 3 greedy steps -> 5-token continuation -> 3 greedy steps."""
+    cfg = preset("toy")
+    sd = numpy_state_dict(cfg, seed=0)
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    model = build_reference(cfg, sd, torch.bfloat16, scratch)
+    ids, pix = synthetic_inputs(cfg, 1, 12, seed=1, dtype=torch.bfloat16)
+    cont, _ = synthetic_inputs(cfg, 1, 12, seed=5, dtype=torch.bfloat16)
+    cont = cont[:, 6:11].contiguous()  # 5 ordinary token ids
+    logits, lens, toks = [], [], []
+    out = model(ids, images=pix, past_key_values=None)
+    for t in range(3):
+        logits.append(out.logits[:, -1].clone()); lens.append(torch.stack([x.clone() for x in out.past_key_values[1]], 0))
+        nxt = out.logits[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
+        out = model(nxt, images=None, past_key_values=out.past_key_values)
+    logits.append(out.logits[:, -1].clone()); lens.append(torch.stack([x.clone() for x in out.past_key_values[1]], 0))
+    out = model(cont, images=None, past_key_values=out.past_key_values)
+    cont_logits = out.logits.clone()
+    lens.append(torch.stack([x.clone() for x in out.past_key_values[1]], 0))
+    for t in range(3):
+        nxt = out.logits[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
+        out = model(nxt, images=None, past_key_values=out.past_key_values)
+        logits.append(out.logits[:, -1].clone()); lens.append(torch.stack([x.clone() for x in out.past_key_values[1]], 0))
+    res = dict(name="toy_bf16_b1_multiround", dtype="torch.bfloat16", B=1, T=12, weight_seed=0, input_seed=1, cont_ids=cont, tokens=toks,
+               step_logits=torch.stack(logits, 0), cont_logits=cont_logits, true_len_hist=torch.stack(lens, 0), preset="toy",
+               kv_shapes=torch.tensor([k.shape[-2] for (k, v) in out.past_key_values[0]]), torch_version=torch.__version__)
+    torch.save(res, os.path.join(out_dir, "multiround_bf16_b1.pt"))
+    print("multiround tokens", toks, "kv", res["kv_shapes"].tolist())
+
+
 if __name__ == "__main__":
     main()
+    with tempfile.TemporaryDirectory(dir=os.path.join(ROOT, "oracle")) as scratch:
+        multiround_case(os.path.join(ROOT, "tests", "golden"), scratch)

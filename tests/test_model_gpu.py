@@ -314,3 +314,41 @@ def test_generate_eos_stops_early_and_text_only_generate():
         model.generate(ids, images=pix, do_sample=True, max_new_tokens=2)
     with pytest.raises(NotImplementedError):
         model.generate(ids, images=pix, num_beams=2, max_new_tokens=2)
+
+
+def test_multiround_continuation_over_ragged_cache():
+    """second user turn (q_len > 1 with a KV cache), pinned to the reference by tests/golden/multiround_bf16_b1.pt"""
+    from tests.test_oracle_golden import _oracle_multiround
+    g0, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b1_natural", out_pred=True)
+    g = torch.load(os.path.join(GOLD, "multiround_bf16_b1.pt"), weights_only=False)
+    rec = {}
+    O.model_forward(sd16, cfg, ids, images=pix, record=rec)
+    keep = rec["keep_index"]
+    # oracle run (bit-exact to the reference) gives the natural decisions; replay tokens + decisions on the GPU
+    logits_ref, cont_ref, lens_ref, toks, _ = _oracle_multiround(sd16, cfg, ids, pix, g)
+    assert toks == g["tokens"]
+    d_all = (lens_ref[1:, -1, 0] - lens_ref[:-1, -1, 0])  # per call: tokens persisted in the last layer
+    out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=keep)
+    got, lens = [out.logits[:, -1].cpu()], [torch.stack(list(out.past_key_values[1]), 0)]
+    past = out.past_key_values
+    for t in range(3):
+        out = model(torch.tensor([[toks[t]]]).cuda(), past_key_values=past, forced_text_decision=torch.tensor([bool(d_all[t])]))
+        past = out.past_key_values
+        got.append(out.logits[:, -1].cpu()); lens.append(torch.stack(list(past[1]), 0))
+    out = model(g["cont_ids"].cuda(), past_key_values=past)
+    past = out.past_key_values
+    cont = out.logits.cpu()
+    lens.append(torch.stack(list(past[1]), 0))
+    for t in range(3):
+        out = model(torch.tensor([[toks[3 + t]]]).cuda(), past_key_values=past, forced_text_decision=torch.tensor([bool(d_all[4 + t])]))
+        past = out.past_key_values
+        got.append(out.logits[:, -1].cpu()); lens.append(torch.stack(list(past[1]), 0))
+    assert torch.equal(torch.stack(lens, 0), g["true_len_hist"])
+    assert [k.shape[-2] for (k, v) in past[0]] == g["kv_shapes"].tolist()
+    scale = g["cont_logits"].abs().max().item()
+    assert cont.shape == g["cont_logits"].shape
+    assert (cont - g["cont_logits"]).abs().max() < 0.04 * scale  # bf16 reference vs bf16 GPU: both carry the bf16 noise floor
+    assert (torch.stack(got, 0) - g["step_logits"]).abs().max() < 0.04 * scale
+    top2 = g["cont_logits"].topk(2, dim=-1).values
+    sure = (top2[..., 0] - top2[..., 1]) > 0.08 * scale
+    assert torch.equal(cont.argmax(-1)[sure], g["cont_logits"].argmax(-1)[sure])
