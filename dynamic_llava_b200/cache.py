@@ -37,6 +37,7 @@ class RaggedKVArena:
         self.host_len_lo = 0  # layers < SL: every token is appended
         self.host_ub_hi = 0   # layers >= SL: upper bound (exact when nothing has been dropped)
         self.hi_exact = True
+        self.floor_lo = self.floor_hi = 0  # host-known lower bounds of kv_len (set at prefill)
 
     def reset(self):
         for t in (self.k_lo, self.v_lo, self.k_hi, self.v_hi, self.kv_len, self.pos, self.step):
@@ -44,6 +45,7 @@ class RaggedKVArena:
         self.keep.fill_(1)
         self.host_len_lo = self.host_ub_hi = 0
         self.hi_exact = True
+        self.floor_lo = self.floor_hi = 0
 
     def layer(self, l: int):
         """-> (K slab [B, heads, cap, hd], V slab, cap)"""

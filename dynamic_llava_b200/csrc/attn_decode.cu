@@ -48,6 +48,10 @@ struct AdFused {
   // weight (o_proj, 33 MB at 7B: fits the 126 MB L2) to be pulled into L2 with a non-blocking bulk prefetch
   const uint8_t* l2_prefetch;
   int64_t l2_prefetch_bytes;
+  // host-known lower bound of every sample's cached length for this layer (the prefill length).  Rows below it were
+  // written long before this decode step, so (n_split == 1 only) the producer may start their TMA loads BEFORE
+  // griddepcontrol.wait, overlapping the K/V fetch with the tail of the QKV GEMM.
+  int len_floor;
 };
 
 __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
@@ -59,12 +63,23 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   AdSmem& S = *reinterpret_cast<AdSmem*>(smem_raw);
   const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
+  int n_pre = 0;  // tiles whose loads were issued before the dependency wait (producer lane only)
+  if (threadIdx.x == AD_CWARPS * 32) {  // the producer lane owns barrier init so that it can start loading immediately
     for (int s = 0; s < AD_STAGES; ++s) {
       mbar_init(&S.full[s], 1);
       mbar_init(&S.empty[s], AD_CWARPS);
     }
     fence_barrier_init();
+    if (n_split == 1) {
+      n_pre = min(AD_STAGES, fz.len_floor / AD_TK);
+      const bf16* kb = k_arena + ((int64_t)b * heads + h) * cap * AD_HD;
+      const bf16* vb = v_arena + ((int64_t)b * heads + h) * cap * AD_HD;
+      for (int t = 0; t < n_pre; ++t) {
+        mbar_expect_tx(&S.full[t], 2 * AD_TK * AD_HD * 2);
+        tma_bulk_g2s(S.kv[t][0], kb + (int64_t)t * AD_TK * AD_HD, AD_TK * AD_HD * 2, &S.full[t]);
+        tma_bulk_g2s(S.kv[t][1], vb + (int64_t)t * AD_TK * AD_HD, AD_TK * AD_HD * 2, &S.full[t]);
+      }
+    }
   }
   pdl_launch_dependents();
   pdl_wait();  // q, side k/v, kv_len and the arena rows of this step come from predecessor kernels
@@ -148,7 +163,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   if (warp == AD_CWARPS) {
     // ---------------- producer warp: TMA bulk copies ----------------
     if (lane == 0) {
-      for (int t = 0; t < n_tiles; ++t) {
+      for (int t = n_pre; t < n_tiles; ++t) {
         const int s = t % AD_STAGES;
         const uint32_t ph = (t / AD_STAGES) & 1;
         mbar_wait(&S.empty[s], ph ^ 1);
@@ -374,7 +389,7 @@ extern "C" int dl_attn_decode_fused(const float* qkv_partial, int n_slices, cons
                                     const void* cos_table, const void* sin_table, void* k_arena, void* v_arena,
                                     const int32_t* kv_len, void* out, void* workspace, int B, int heads, int head_dim, int cap,
                                     int n_split, float scale, int quirk_pad, const void* l2_prefetch, int64_t l2_prefetch_bytes,
-                                    cudaStream_t stream) {
+                                    int len_floor, cudaStream_t stream) {
   DL_REQUIRE(head_dim == AD_HD && n_split >= 1 && (n_split == 1 || workspace != nullptr) && qkv_partial != nullptr,
              "dl_attn_decode_fused");
   if (B == 0) return 0;
@@ -397,6 +412,7 @@ extern "C" int dl_attn_decode_fused(const float* qkv_partial, int n_slices, cons
   fz.v_arena_w = (bf16*)v_arena;
   fz.l2_prefetch = (const uint8_t*)l2_prefetch;
   fz.l2_prefetch_bytes = l2_prefetch_bytes;
+  fz.len_floor = len_floor > 0 ? len_floor : 0;
   dl_launch_pdl(attn_decode_kernel, dim3(heads, B, n_split), dim3(AD_THREADS), sizeof(AdSmem), stream, (const bf16*)nullptr, 0,
                 (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)nullptr, (const bf16*)nullptr, kv_len, (bf16*)out, ws_acc, ws_ml,
                 B, heads, cap, n_split, scale, quirk_pad, fz);

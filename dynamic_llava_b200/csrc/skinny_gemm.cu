@@ -16,7 +16,7 @@
 
 #define SG_BM 128
 #define SG_BK 64
-#define SG_STAGES 5
+#define SG_STAGES 5  // 6 stages (110 KB, still 2 CTAs/SM) measured no faster: profiles/r1_microbench_v8_skinny_6stage.json
 #define SG_THREADS 192  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 
 template <int NB>
@@ -45,9 +45,12 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * SG_BM;  // EPI == 1: tile j = blockIdx.x covers SwiGLU outputs [64j, 64j+64)
   const int split = blockIdx.y;
-  const int kb0 = split * kb_per_split;
-  const int kb1 = min(KB, kb0 + kb_per_split);
+  // balanced K partition: split s owns k-blocks [s*KB/S, (s+1)*KB/S) (sizes differ by at most one block)
+  const int n_splits = gridDim.y;
+  const int kb0 = (int)(((int64_t)split * KB) / n_splits);
+  const int kb1 = (int)(((int64_t)(split + 1) * KB) / n_splits);
   const int nkb = kb1 - kb0;
+  (void)kb_per_split;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -232,8 +235,7 @@ extern "C" int dl_skinny_gemm_splits(int N, int K, int target_ctas) {
   if (max_s < 1) max_s = 1;
   if (s > max_s) s = max_s;
   if (s > 8) s = 8;  // consumers fetch the slices in one 8-deep group of loads
-  const int kbps = (KB + s - 1) / s;
-  return (KB + kbps - 1) / kbps;  // effective number of non-empty splits
+  return s;
 }
 
 extern "C" int dl_skinny_gemm(const void* x, const void* w, float* partial, int M, int N, int K, int splits, int l2_prefetch_mb,
@@ -241,7 +243,7 @@ extern "C" int dl_skinny_gemm(const void* x, const void* w, float* partial, int 
   DL_REQUIRE(M >= 1 && M <= 64 && K % SG_BK == 0 && N % 8 == 0 && splits >= 1, "dl_skinny_gemm");
   const int KB = K / SG_BK;
   const int kbps = (KB + splits - 1) / splits;
-  DL_REQUIRE((splits - 1) * kbps < KB, "dl_skinny_gemm(empty split)");
+  DL_REQUIRE(splits <= KB, "dl_skinny_gemm(empty split)");
   const int NB = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
   alignas(64) CUtensorMap tw, tx;
   int rc = dl_make_tmap_2d(&tw, w, (uint64_t)N, (uint64_t)K, (uint64_t)K, SG_BM, SG_BK);

@@ -91,6 +91,7 @@ class Engine:
         self.packed_attn = os.environ.get("DLB200_PACKED_ATTN", "tc")  # CLIP / predictor attention: "tc" (tcgen05) | "mma"
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
+        self.attn_early_kv = os.environ.get("DLB200_ATTN_EARLY_KV", "1") == "1"  # fetch prefill-time K/V tiles before the PDL wait
         self.attn_prefetch_wo = os.environ.get("DLB200_ATTN_PREFETCH_WO", "0") == "1"  # o_proj weight -> L2 during decode attention (measured: no gain)
         self.launches = 0  # kernels of OURS launched (eager path; graph replays counted via launches_per_step)
         self.launches_per_step = 0
@@ -443,6 +444,7 @@ class Engine:
         self.launches += 1
         a.host_len_lo += P
         a.host_ub_hi += Lq
+        a.floor_lo, a.floor_hi = a.host_len_lo, a.host_ub_hi  # every sample holds at least the prefill tokens from here on
         if all_logits:
             xn = self.rmsnorm(x, m.norm.weight, c.rms_norm_eps)
             return F.linear(xn, self.model.lm_head.weight).view(B, Lq, -1)
@@ -528,7 +530,8 @@ class Engine:
             L_.attn_decode_fused(_p(sess.partial), s, _p(a.pos), _p(keep if l >= SL else None), _p(pk["cos"]), _p(pk["sin"]), _p(K_), _p(V_),
                                  _p(kvl), _p(sess.attn), _p(sess.attn_ws), B, nh, hd, cap, ns, scale,
                                  1 if (quirk and l >= SL and keep is not None) else 0,
-                                 _p(W["wo"]) if self.attn_prefetch_wo else None, W["wo"].numel() * 2, st)
+                                 _p(W["wo"]) if self.attn_prefetch_wo else None, W["wo"].numel() * 2,
+                                 (a.floor_lo if l < SL else a.floor_hi) if self.attn_early_kv else 0, st)
             s = self._gemm(sess, sess.attn, W["wo"], B, H, H)
             L_.dec_reduce_residual_norm(_p(sess.partial), _p(sess.xres), _p(W["ln2"]), _p(sess.xn), B, H, s, eps, st)
             L_.skinny_gemm_swiglu(_p(sess.xn), _p(W["wgu"]), _p(sess.act), B, I, H, st)  # gate|up GEMM with SwiGLU in the epilogue

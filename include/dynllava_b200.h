@@ -108,8 +108,10 @@ int dl_attn_decode(const void* q, int q_row_stride, const void* k_arena, const v
 int dl_attn_decode_fused(const float* qkv_partial, int n_slices, const int32_t* pos, const uint8_t* keep, const void* cos_table,
                          const void* sin_table, void* k_arena, void* v_arena, const int32_t* kv_len, void* out, void* workspace,
                          int B, int heads, int head_dim, int cap, int n_split, float scale, int quirk_pad, const void* l2_prefetch,
-                         int64_t l2_prefetch_bytes, cudaStream_t stream);
-/* l2_prefetch (or NULL): device range (the next GEMM's weight) the CTAs ask the TMA unit to pull into L2 while they run. */
+                         int64_t l2_prefetch_bytes, int len_floor, cudaStream_t stream);
+/* l2_prefetch (or NULL): device range (the next GEMM's weight) the CTAs ask the TMA unit to pull into L2 while they run.
+ * len_floor: host-known lower bound of every kv_len[b] (the prefill length; 0 = unknown): K/V tiles below it are fetched
+ * before the kernel waits on its predecessor. */
 
 /* ---- K2/K6/K7: variable-length attention (warp-MMA tile path), DML:1114-1122; CTL:164-169; HF CLIPAttention ---- */
 /* Addresses: Q(b,i,h) = q + (cu_q[b]+i)*q_tok_stride + h*q_head_stride;

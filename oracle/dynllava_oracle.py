@@ -515,3 +515,24 @@ def hf_greedy_generate(sd: StateDict, cfg: dict, input_ids: Tensor, images: Tens
         if eos_token_id is not None and int(unfinished.max()) == 0:
             break
     return torch.stack(out, 1)
+
+
+@torch.no_grad()
+def multiround_loop(sd, cfg, ids, pix, cont_ids):
+    """prefill -> 3 greedy steps -> multi-token continuation (new user turn) -> 3 greedy steps: the call pattern of
+    llava/dynamic_eval/model_lvis_multi_round_for_meteor.py:150-185 (mirrors oracle/gen_golden.py:multiround_case)."""
+    logits, lens, toks = [], [], []
+    lg, past = model_forward(sd, cfg, ids, images=pix)
+    for t in range(3):
+        logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
+        nxt = lg[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
+        lg, past = model_forward(sd, cfg, nxt, past=past)
+    logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
+    cont_lg, past = model_forward(sd, cfg, cont_ids, past=past)
+    lens.append(torch.stack(list(past[1]), 0).clone())
+    lg = cont_lg
+    for t in range(3):
+        nxt = lg[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
+        lg, past = model_forward(sd, cfg, nxt, past=past)
+        logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
+    return torch.stack(logits, 0), cont_lg, torch.stack(lens, 0), toks, past

@@ -318,14 +318,13 @@ def test_generate_eos_stops_early_and_text_only_generate():
 
 def test_multiround_continuation_over_ragged_cache():
     """second user turn (q_len > 1 with a KV cache), pinned to the reference by tests/golden/multiround_bf16_b1.pt"""
-    from tests.test_oracle_golden import _oracle_multiround
     g0, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b1_natural", out_pred=True)
     g = torch.load(os.path.join(GOLD, "multiround_bf16_b1.pt"), weights_only=False)
     rec = {}
     O.model_forward(sd16, cfg, ids, images=pix, record=rec)
     keep = rec["keep_index"]
     # oracle run (bit-exact to the reference) gives the natural decisions; replay tokens + decisions on the GPU
-    logits_ref, cont_ref, lens_ref, toks, _ = _oracle_multiround(sd16, cfg, ids, pix, g)
+    logits_ref, cont_ref, lens_ref, toks, _ = O.multiround_loop(sd16, cfg, ids, pix, g["cont_ids"])
     assert toks == g["tokens"]
     d_all = (lens_ref[1:, -1, 0] - lens_ref[:-1, -1, 0])  # per call: tokens persisted in the last layer
     out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=keep)

@@ -98,24 +98,6 @@ def test_hf_greedy_generate_semantics(golden_dir):
     assert torch.equal(out[0], g["tokens"][0][: out.shape[1]])
 
 
-def _oracle_multiround(sd, cfg, ids, pix, g):
-    logits, lens, toks = [], [], []
-    lg, past = O.model_forward(sd, cfg, ids, images=pix)
-    for t in range(3):
-        logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
-        nxt = lg[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
-        lg, past = O.model_forward(sd, cfg, nxt, past=past)
-    logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
-    cont_lg, past = O.model_forward(sd, cfg, g["cont_ids"], past=past)
-    lens.append(torch.stack(list(past[1]), 0).clone())
-    lg = cont_lg
-    for t in range(3):
-        nxt = lg[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
-        lg, past = O.model_forward(sd, cfg, nxt, past=past)
-        logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
-    return torch.stack(logits, 0), cont_lg, torch.stack(lens, 0), toks, past
-
-
 def test_multiround_continuation_matches_reference_bitexact(golden_dir):
     """second user turn: q_len > 1 over a ragged cache (use_instruct_predictor=False as in README.md:110)"""
     g = torch.load(os.path.join(golden_dir, "multiround_bf16_b1.pt"), weights_only=False)
@@ -123,7 +105,7 @@ def test_multiround_continuation_matches_reference_bitexact(golden_dir):
     cfg["sparse_config"]["use_output_text_predictor"] = True
     sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, seed=0).items()}
     ids, pix = synthetic_inputs(cfg, 1, 12, seed=1, dtype=torch.bfloat16)
-    logits, cont_lg, lens, toks, past = _oracle_multiround(sd, cfg, ids, pix, g)
+    logits, cont_lg, lens, toks, past = O.multiround_loop(sd, cfg, ids, pix, g["cont_ids"])
     assert toks == g["tokens"]
     assert torch.equal(cont_lg, g["cont_logits"]) and torch.equal(logits, g["step_logits"])
     assert torch.equal(lens, g["true_len_hist"])
