@@ -25,6 +25,7 @@ SOURCES = [
     "attn_prefill_mma.cu",
     "attn_prefill_tc.cu",
     "attn_prefill_tc2.cu",
+    "attn_prefill_tc3.cu",
     "skinny_gemm.cu",
     "gemm_tc.cu",
     "decode_fused.cu",

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_prefill_tc_kernel(
 
   if (warp == 4) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       mbar_expect_tx(&S.bar_q, TC_TILE_BYTES);
       tma_load_2d(S.q, &tmap_q, h * TC_HD, q_start + m0, &S.bar_q);
       tma_load_2d(S.q + TC_TILE_BYTES / 2, &tmap_q, h * TC_HD + 64, q_start + m0, &S.bar_q);
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_prefill_tc_kernel(
     }
   } else if (warp == 5) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(S.q), p_addr = smem_u32(S.p);

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       mbar_expect_tx(&S.q_full, (b_active ? 2 : 1) * T2_TILE_BYTES);
 #pragma unroll
       for (int x = 0; x < NBOX; ++x) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) attn_prefill_tc2_kernel(
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, HD, 0, 1);  // N = head_dim; B (= V) MN-major
       auto issue_s = [&](int g, int j) {

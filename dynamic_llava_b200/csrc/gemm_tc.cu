@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const __grid_consta
   const uint32_t tmem_d = S.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       constexpr uint32_t BYTES = (GT_BM + GT_BN) * GT_BK * 2;
       for (int i = 0; i < KB; ++i) {
         const int s = i % GT_STAGES;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_tc_kernel(const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       constexpr uint32_t IDESC = umma_idesc_bf16(GT_BM, GT_BN);
       for (int i = 0; i < KB; ++i) {
         const int s = i % GT_STAGES;

@@ -4,16 +4,42 @@
 // ORIGINAL (pre-drop) positions, and a CSR header (cu_seqlens) describes the packed result.
 //
 // Grid = (R, B).  Every CTA of sample b redoes the selection for its sample in shared memory — an O(n) two-pass radix
-// select on the 16-bit score keys (256-bin histogram of the high byte, then of the low byte inside the boundary bin),
-// followed by an ordered compaction scan; ~2 us, so replicating it per CTA is cheaper than a second kernel or a round
-// trip of the index map through HBM — and then streams its share of the P' output rows with 128-bit no-allocate
-// loads/stores.  Ties at the k-th score are broken towards the lower index (= stable descending sort).
+// select on the 16-bit score keys (256-bin histogram of the high byte, then of the low byte inside the boundary bin,
+// warp-aggregated with match.any so equal keys cost one shared atomic per warp), followed by an ordered compaction
+// scan; replicating it per CTA is cheaper than a second kernel or a round trip of the index map through HBM.
+// The rows move through a shared-memory ring of whole-row slots driven by ONE thread with bulk async copies
+// (cp.async.bulk global->shared on an mbarrier, shared->global in bulk groups): no register staging, 64 KB in flight per
+// CTA.  Rows are visited text-first: the [left | right] text rows do not depend on the selection, so their loads are
+// issued BEFORE the selection runs and the radix select hides under the first HBM round trip.
+// Ties at the k-th score are broken towards the lower index (= stable descending sort).
 // HBM-bound: algorithmic bytes = 2 * B * P' * H * 2.
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
 
 #define SC_THREADS 256
 #define SC_MAX_IMG 1024
+#define SC_MAX_SLOTS 16
+#define SC_RING_BYTES 65536
+
+// shared -> global bulk copy (async proxy), tracked by bulk groups
+DL_DEVINL void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+DL_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+DL_DEVINL void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// histogram update where lanes holding the same bin share one shared-memory atomic
+DL_DEVINL void hist_add_aggregated(int* hist, int bin, bool valid) {
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const unsigned peers = __match_any_sync(act, bin);
+    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+  }
+}
 
 __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
     const bf16* __restrict__ logits,         // [B, n_img, 2]
@@ -23,14 +49,39 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
     int64_t* __restrict__ keep_index,        // [B, k]
     int32_t* __restrict__ pos_out,           // [B, P']
     int32_t* __restrict__ cu_seqlens,        // [B + 1]
-    int P, int H, int s0, int n_img, int k) {
+    int P, int H, int s0, int n_img, int k, int n_slots) {
+  extern __shared__ __align__(128) uint8_t ring[];  // n_slots whole rows
+  __shared__ __align__(8) uint64_t full[SC_MAX_SLOTS];
   __shared__ uint16_t key[SC_MAX_IMG];
   __shared__ int16_t kidx[SC_MAX_IMG];
   __shared__ int hist[256];
   __shared__ int wsum[SC_THREADS / 32];
   __shared__ int sel[4];  // [0] boundary bin, [1] #keys above it
   const int b = blockIdx.y, tid = threadIdx.x;
+  const int R = gridDim.x, r = blockIdx.x;
   const int Pp = P - n_img + k;
+  const int n_text = Pp - k;
+  const uint32_t row_bytes = (uint32_t)H * 2u;
+  const bf16* in_b = hid_in + (int64_t)b * P * H;
+  bf16* out_b = hid_out + (int64_t)b * Pp * H;
+  // this CTA's rows in text-first order: v = r, r + R, ...; v < n_text is text row v (left part, then right part),
+  // v >= n_text is kept image row v - n_text
+  const int n_mine = r < Pp ? (Pp - r + R - 1) / R : 0;
+  int issued = 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < n_slots; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+    // text rows need no selection: start their loads now
+    while (issued < n_mine && issued < n_slots) {
+      const int v = r + issued * R;
+      if (v >= n_text) break;
+      const int sj = v < s0 ? v : v + n_img;
+      mbar_expect_tx(&full[issued], row_bytes);
+      tma_bulk_g2s(ring + (size_t)issued * row_bytes, in_b + (int64_t)sj * H, row_bytes, &full[issued]);
+      ++issued;
+    }
+  }
 
   if (forced_keep != nullptr) {
     for (int i = tid; i < k; i += SC_THREADS) kidx[i] = (int16_t)forced_keep[(int64_t)b * k + i];
@@ -47,15 +98,16 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
     }
     // two radix passes: find T = the k-th largest key, c_gt = #keys > T
     int prefix = 0, c_gt = 0, want = k;
+    const int n_round = (n_img + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
     for (int pass = 0; pass < 2; ++pass) {
       if (tid < 256) hist[tid] = 0;
       __syncthreads();
-      for (int i = tid; i < n_img; i += SC_THREADS) {
-        const int kk = key[i];
+      for (int i = tid; i < n_round; i += SC_THREADS) {  // whole warps stay converged for match.any
+        const int kk = i < n_img ? key[i] : 0;
         if (pass == 0)
-          atomicAdd(&hist[kk >> 8], 1);
-        else if ((kk >> 8) == prefix)
-          atomicAdd(&hist[kk & 255], 1);
+          hist_add_aggregated(hist, kk >> 8, i < n_img);
+        else
+          hist_add_aggregated(hist, kk & 255, i < n_img && (kk >> 8) == prefix);
       }
       __syncthreads();
       if (tid < 32) {  // suffix scan over the 256 bins (8 per lane), locate the bin that holds the `want`-th largest
@@ -116,45 +168,36 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
   }
   __syncthreads();
 
-  if (blockIdx.x == 0) {  // index map + CSR header
-    for (int i = tid; i < k; i += SC_THREADS) keep_index[(int64_t)b * k + i] = kidx[i];
-    for (int j = tid; j < Pp; j += SC_THREADS) {
+  if (tid == 0) {
+    // ---- copy engine: ring of whole-row slots, loads n_slots - 1 deep, stores in bulk groups ----
+    auto src_row = [&](int v) { return v < n_text ? (v < s0 ? v : v + n_img) : s0 + (int)kidx[v - n_text]; };
+    auto dst_row = [&](int v) { return v < n_text ? (v < s0 ? v : v + k) : s0 + (v - n_text); };
+    auto issue_load = [&](int i) {
+      const int s = i % n_slots;
+      mbar_expect_tx(&full[s], row_bytes);
+      tma_bulk_g2s(ring + (size_t)s * row_bytes, in_b + (int64_t)src_row(r + i * R) * H, row_bytes, &full[s]);
+    };
+    while (issued < n_mine && issued < n_slots) issue_load(issued++);
+    for (int i = 0; i < n_mine; ++i) {
+      const int s = i % n_slots;
+      mbar_wait(&full[s], (uint32_t)(i / n_slots) & 1u);
+      bulk_s2g(out_b + (int64_t)dst_row(r + i * R) * H, ring + (size_t)s * row_bytes, row_bytes);
+      bulk_commit();
+      if (i >= 1 && issued < n_mine) {  // slot of row i-1 is free once its store has read it
+        bulk_wait_read<1>();
+        issue_load(issued++);
+      }
+    }
+    bulk_wait_read<0>();
+  } else if (r == 0) {  // index map + CSR header
+    for (int i = tid - 1; i < k; i += SC_THREADS - 1) keep_index[(int64_t)b * k + i] = kidx[i];
+    for (int j = tid - 1; j < Pp; j += SC_THREADS - 1) {
       int p = j < s0 ? j : (j < s0 + k ? s0 + kidx[j - s0] : j + (n_img - k));
       pos_out[(int64_t)b * Pp + j] = p;
     }
-    if (tid == 0) {
+    if (tid == 1) {
       cu_seqlens[b + 1] = (b + 1) * Pp;
       if (b == 0) cu_seqlens[0] = 0;
-    }
-  }
-
-  // streamed row gather: 2 rows in flight per iteration
-  const int nchunk = H >> 3;
-  const bf16* in_b = hid_in + (int64_t)b * P * H;
-  bf16* out_b = hid_out + (int64_t)b * Pp * H;
-  for (int j = blockIdx.x; j < Pp; j += 2 * gridDim.x) {
-    const int j2 = j + gridDim.x;
-    const int sj = j < s0 ? j : (j < s0 + k ? s0 + kidx[j - s0] : j + (n_img - k));
-    const bool has2 = j2 < Pp;
-    const int sj2 = !has2 ? sj : (j2 < s0 ? j2 : (j2 < s0 + k ? s0 + kidx[j2 - s0] : j2 + (n_img - k)));
-    const bf16* a = in_b + (int64_t)sj * H;
-    const bf16* a2 = in_b + (int64_t)sj2 * H;
-    bf16* o = out_b + (int64_t)j * H;
-    bf16* o2 = out_b + (int64_t)j2 * H;
-    for (int c = tid; c < nchunk; c += 2 * SC_THREADS) {
-      const int c2 = c + SC_THREADS;
-      int4 v0 = ld_stream(a + c * 8), v1, v2, v3;
-      if (c2 < nchunk) v1 = ld_stream(a + c2 * 8);
-      if (has2) {
-        v2 = ld_stream(a2 + c * 8);
-        if (c2 < nchunk) v3 = ld_stream(a2 + c2 * 8);
-      }
-      st_stream(o + c * 8, v0);
-      if (c2 < nchunk) st_stream(o + c2 * 8, v1);
-      if (has2) {
-        st_stream(o2 + c * 8, v2);
-        if (c2 < nchunk) st_stream(o2 + c2 * 8, v3);
-      }
     }
   }
 }
@@ -162,16 +205,28 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
 extern "C" int dl_select_compact(const void* logits, const int64_t* forced_keep, const void* hidden_in, void* hidden_out,
                                  int64_t* keep_index, int32_t* pos_out, int32_t* cu_seqlens, int B, int P, int H,
                                  int img_start, int n_img, int k, int ctas_per_sample, cudaStream_t stream) {
-  DL_REQUIRE(H % 8 == 0 && n_img <= SC_MAX_IMG && k >= 0 && k <= n_img && img_start >= 0 && img_start + n_img <= P,
+  DL_REQUIRE(H % 8 == 0 && H * 2 <= SC_RING_BYTES && n_img <= SC_MAX_IMG && k >= 0 && k <= n_img && img_start >= 0 &&
+                 img_start + n_img <= P,
              "dl_select_compact");
+  DL_REQUIRE((((uintptr_t)hidden_in | (uintptr_t)hidden_out) & 15) == 0, "dl_select_compact (16-byte aligned rows)");
   if (B == 0) return 0;
   const int Pp = P - n_img + k;
+  if (Pp == 0) return 0;
+  int n_slots = SC_RING_BYTES / (H * 2);
+  if (n_slots > SC_MAX_SLOTS) n_slots = SC_MAX_SLOTS;
+  const int smem = n_slots * H * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(select_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_RING_BYTES);
+    if (e != cudaSuccess) return dl_set_error((int)e, "dl_select_compact(smem attr)");
+    attr_set = true;
+  }
   int R = ctas_per_sample;
-  if (R <= 0) R = (148 * 8 + B - 1) / B;  // ~8 resident CTAs per SM worth of rows in flight
+  if (R <= 0) R = (148 * 3 + B - 1) / B;  // three 64 KB rings resident per SM
   if (R > Pp) R = Pp;
   if (R < 1) R = 1;
-  select_compact_kernel<<<dim3(R, B), SC_THREADS, 0, stream>>>((const bf16*)logits, forced_keep, (const bf16*)hidden_in,
-                                                               (bf16*)hidden_out, keep_index, pos_out, cu_seqlens, P, H,
-                                                               img_start, n_img, k);
+  select_compact_kernel<<<dim3(R, B), SC_THREADS, smem, stream>>>((const bf16*)logits, forced_keep, (const bf16*)hidden_in,
+                                                                  (bf16*)hidden_out, keep_index, pos_out, cu_seqlens, P, H,
+                                                                  img_start, n_img, k, n_slots);
   DL_CHECK_LAUNCH("dl_select_compact");
 }

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
   const uint32_t tmem_d = S.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       constexpr uint32_t BYTES = (SG_BM + NB) * SG_BK * 2;
       // The weights do not depend on the previous kernel: start streaming W into every free stage right away, and only
       // then wait for the predecessor (PDL) before fetching the activation tiles X it produced.
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
       constexpr uint32_t IDESC = umma_idesc_bf16(SG_BM, NB);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % SG_STAGES;

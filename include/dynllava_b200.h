@@ -138,6 +138,15 @@ int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena
 int dl_attn_packed_tc(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
                       int max_q_len, float scale, cudaStream_t stream);
 
+/* K2 v3 / K6-K7 v3: same contracts as dl_attn_prefill_tc2 / dl_attn_packed_tc; 64-key half tiles with double-buffered S in
+ * TMEM so that softmax and tensor pipe never wait on each other's latency (attn_prefill_tc3.cu).  flags bit 0: one exp2 in
+ * four on the FMA pipe (degree-3 polynomial, rel. error 7.5e-5) instead of the SFU. */
+int dl_attn_prefill_tc3(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
+                        int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
+                        int cap, int max_q_len, float scale, int flags, cudaStream_t stream);
+int dl_attn_packed_tc3(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
+                       int max_q_len, float scale, int flags, cudaStream_t stream);
+
 /* ---- decode-step weight streaming: every nn.Linear at q_len == 1 (DML:1011-1013, :1127, :328, :2709) ----------- */
 /* partial fp32 [splits, M, N] = per-split X[M,K] . W[N,K]^T; M <= 64, K % 64 == 0.  TMA + tcgen05.
  * l2_prefetch_mb: bytes of W (total over the grid) each launch asks the TMA unit to pull into L2 ahead of its smem ring

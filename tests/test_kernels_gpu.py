@@ -532,6 +532,63 @@ def test_attn_prefill_pingpong_rescale_path(L, which):
     assert (out.float().cpu() - ref).abs().max() < 3e-2 * max(1.0, ref.abs().max().item())
 
 
+def _call_tc3(L, flags):
+    def fn(qkv, K, V, out, cu, past, N, B, nh, hd, cap, max_q, causal):
+        assert causal and hd == 128
+        H = nh * hd
+        L.attn_prefill_tc3(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), N, B, nh, cap, max_q, 1.0 / math.sqrt(hd), flags, ST())
+    return fn
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("q_lens,pasts", [([128], [0]), ([256], [0]), ([1], [0]), ([63, 64, 65], [0, 0, 0]), ([146, 146], [0, 0]),
+                                          ([607, 33, 129, 300], [0, 0, 0, 0]), ([19, 70], [27, 5]), ([1587], [0]), ([300], [500]),
+                                          ([200, 257], [64, 63])])
+def test_attn_prefill_tcgen05_double_buffered(L, q_lens, pasts, flags):
+    """K2 v3: 64-key half tiles, two S buffers per group; flags=1 evaluates a quarter of the exp2 with the FMA polynomial."""
+    _varlen_case(L, _call_tc3(L, flags), 128, True, q_lens, pasts, nh=2)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("B,N,nh", [(2, 577, 16), (3, 576, 8), (2, 17, 2), (1, 300, 4), (2, 64, 1), (1, 129, 2)])
+def test_attn_packed_tc3_noncausal_hd64(L, B, N, nh, flags):
+    """CLIP (577 tokens, 16 heads) and predictor (576 tokens, 8 heads) attention on the v3 pipeline vs fp32 attention."""
+    hd = 64
+    C = nh * hd
+    qkv = rnd(B * N, 3 * C, seed=91)
+    out = torch.full((B * N, C), float("nan"), device=DEV, dtype=BF)
+    cu = torch.arange(0, (B + 1) * N, N, dtype=torch.int32, device=DEV)
+    L.attn_packed_tc3(P(qkv.to(DEV)), P(out), P(cu), B * N, B, nh, hd, N, 1.0 / math.sqrt(hd), flags, ST())
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    for b in range(B):
+        for h in range(nh):
+            sl = slice(b * N, (b + 1) * N)
+            ref = _sdpa_ref(qkv[sl, h * hd:(h + 1) * hd], qkv[sl, C + h * hd:C + (h + 1) * hd], qkv[sl, 2 * C + h * hd:2 * C + (h + 1) * hd])
+            assert (got[sl, h * hd:(h + 1) * hd] - ref).abs().max() < 2e-2, (b, h)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_attn_prefill_tc3_rescale_path(L, flags):
+    """keys whose scores grow by far more than 2^8 along the sequence force the lazy O-rescale branch"""
+    B, nh, hd, Lq = 1, 1, 128, 512
+    H = nh * hd
+    qkv = torch.zeros(Lq, 3 * H, dtype=BF)
+    qkv[:, 0] = 8.0  # q = 8 * e0
+    K = torch.zeros(B, nh, Lq + 4, hd, dtype=BF)
+    V = rnd(B, nh, Lq + 4, hd, seed=95)
+    K[0, 0, :Lq, 0] = torch.linspace(-30, 30, Lq).to(BF)  # logits = 64 * k0 / sqrt(128): span ~ +-170
+    out = torch.zeros(Lq, H, device=DEV, dtype=BF)
+    cu = torch.tensor([0, Lq], dtype=torch.int32, device=DEV)
+    past = torch.zeros(1, dtype=torch.int32, device=DEV)
+    L.attn_prefill_tc3(P(qkv.to(DEV)), 3 * H, P(K.to(DEV)), P(V.to(DEV)), P(out), H, P(cu), P(past), Lq, B, nh, Lq + 4, Lq,
+                       1.0 / math.sqrt(hd), flags, ST())
+    torch.cuda.synchronize()
+    ref = _sdpa_ref(qkv[:, :hd], K[0, 0, :Lq], V[0, 0, :Lq], causal_off=0)
+    assert (out.float().cpu() - ref).abs().max() < 3e-2 * max(1.0, ref.abs().max().item())
+
+
 # ---------------------------------------------------------------------------------------------- decode weight streaming
 @pytest.mark.parametrize("M,N,K,splits", [(8, 768, 256, 1), (8, 512, 512, 2), (1, 12288, 4096, 3), (8, 4096, 11008, 9), (16, 22016, 4096, 2),
                                           (3, 32000, 4096, 1), (24, 4096, 4096, 8), (64, 1024, 4096, 4)])

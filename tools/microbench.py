@@ -114,6 +114,13 @@ def bench_attn_prefill(out):
         o_tc = o.clone()
         ms_tc2 = timeit(lambda i: L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, ST()), 1)
         diff2 = (o.float() - o_tc.float()).abs().max().item()
+        t3 = {}
+        for fl in (0, 1):
+            ms3 = timeit(lambda i: L.attn_prefill_tc3(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, fl, ST()), 1)
+            t3[f"tc3_f{fl}_us"] = ms3 * 1e3
+            t3[f"tc3_f{fl}_TFLOPs"] = flop / ms3 / 1e9
+            t3[f"tc3_f{fl}_frac_of_sustained_bf16"] = flop / ms3 / 1e9 / pk["bf16_tflops_sustained"]
+            t3[f"tc3_f{fl}_vs_tc_maxdiff"] = (o.float() - o_tc.float()).abs().max().item()
         ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * H, hd, P(K), P(V), nh * cap * hd, cap * hd, hd, 0, P(o), H, P(cu), P(past), B, nh, hd, Lq, 1, sc, ST()), 1)
         diff = (o.float() - o_tc.float()).abs().max().item()
         q4 = qkv[:, :H].view(B, Lq, nh, hd).transpose(1, 2)
@@ -123,7 +130,7 @@ def bench_attn_prefill(out):
                      "frac_of_sustained_bf16": flop / ms_tc / 1e9 / pk["bf16_tflops_sustained"], "mma_us": ms_mma * 1e3,
                      "mma_TFLOPs": flop / ms_mma / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "torch_sdpa_TFLOPs": flop / ms_sdpa / 1e9,
                      "tc_vs_mma_maxdiff": diff, "tc2_us": ms_tc2 * 1e3, "tc2_TFLOPs": flop / ms_tc2 / 1e9,
-                     "tc2_frac_of_sustained_bf16": flop / ms_tc2 / 1e9 / pk["bf16_tflops_sustained"], "tc2_vs_tc_maxdiff": diff2})
+                     "tc2_frac_of_sustained_bf16": flop / ms_tc2 / 1e9 / pk["bf16_tflops_sustained"], "tc2_vs_tc_maxdiff": diff2, **t3})
         print("ATTN_PREFILL", rows[-1], flush=True)
     out["attn_prefill"] = rows
     rows = []
@@ -136,13 +143,19 @@ def bench_attn_prefill(out):
         sc = 1.0 / math.sqrt(hd)
         ms_tc = timeit(lambda i: L.attn_packed_tc(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, ST()), 1)
         o1 = o.clone()
+        t3 = {}
+        for fl in (0, 1):
+            ms3 = timeit(lambda i: L.attn_packed_tc3(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, fl, ST()), 1)
+            t3[f"tc3_f{fl}_us"] = ms3 * 1e3
+            t3[f"tc3_f{fl}_TFLOPs"] = flop / ms3 / 1e9
+            t3[f"tc3_f{fl}_vs_tc2_maxdiff"] = (o.float() - o1.float()).abs().max().item()
         kp = ctypes.c_void_p(qkv.data_ptr() + C * 2)
         vp = ctypes.c_void_p(qkv.data_ptr() + 2 * C * 2)
         ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * C, hd, kp, vp, 0, hd, 3 * C, 1, P(o), C, P(cu), None, B, nh, hd, N, 0, sc, ST()), 1)
         q4 = qkv.view(B, N, 3, nh, hd).permute(2, 0, 3, 1, 4)
         ms_sdpa = timeit(lambda i: F.scaled_dot_product_attention(q4[0], q4[1], q4[2]), 1)
         rows.append({"case": name, "GFLOP": flop / 1e9, "tcgen05_us": ms_tc * 1e3, "tcgen05_TFLOPs": flop / ms_tc / 1e9, "mma_us": ms_mma * 1e3,
-                     "mma_TFLOPs": flop / ms_mma / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "maxdiff_tc_vs_mma": (o.float() - o1.float()).abs().max().item()})
+                     "mma_TFLOPs": flop / ms_mma / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "maxdiff_tc_vs_mma": (o.float() - o1.float()).abs().max().item(), **t3})
         print("ATTN_PACKED", rows[-1], flush=True)
     out["attn_packed_hd64"] = rows
 
