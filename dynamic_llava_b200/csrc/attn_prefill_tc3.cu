@@ -8,10 +8,11 @@
 // pipe idled while the group digested it.  v3 breaks the chain by working on 64-key HALF tiles with two S buffers per
 // group: S(j+1) is already complete in TMEM when softmax(j) ends, and S(j+2) is issued right behind PV(j).
 //
-// One CTA = (256 query rows = two 128-row tiles A and B, one head, one sample); 352 threads:
+// One CTA = (256 query rows = two 128-row tiles A and B, one head, one sample); 384 threads:
 //   warp 0      K producer (+Q): 128-key K tiles by TMA into a 2-stage ring (HD/64 SW128 boxes each);
 //   warp 10     V producer: same for V (K and V stages are released at different times, so they have their own rings);
-//   warp 1      MMA issuer (one thread).  Per 64-key half j:  PV_A(j) S_A(j+2) PV_B(j) S_B(j+2);
+//   warp 1, 11  MMA issuers, one thread per group (a single issuer would park group A's ready MMAs behind its wait for
+//               group B's P).  Per 64-key half j:  PV(j) S(j+2);
 //   warps 2-5   softmax group A, warps 6-9 softmax group B: one thread per query row (TMEM lane == row).
 // TMEM: S_A0 [0,64) S_A1 [64,128) S_B0 [128,192) S_B1 [192,256) O_A [256,256+HD) O_B [256+HD,256+2HD).
 //   * S(j) lives in buffer j&1; it is read ONCE into registers, P = exp2(S*scale - m) is written back as packed bf16 over
@@ -25,7 +26,7 @@
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
 
-#define T3_THREADS 352
+#define T3_THREADS 384
 #define T3_RESCALE_LOG2 8.0f
 
 #ifdef DL_T3_TRACE
@@ -54,8 +55,8 @@ struct T3Smem {
   alignas(8) uint64_t q_full;
   alignas(8) uint64_t k_full[2];
   alignas(8) uint64_t v_full[2];
-  alignas(8) uint64_t k_empty[2];
-  alignas(8) uint64_t v_empty[2];
+  alignas(8) uint64_t k_empty[2][2];  // [group][stage]: each group's issuer releases the stages it has read
+  alignas(8) uint64_t v_empty[2][2];
   alignas(8) uint64_t s_full[2][2];  // [group][buffer]
   alignas(8) uint64_t p_full[2][2];
   alignas(8) uint64_t o_done[2][2];  // [group][half parity]: with the S look-ahead a single barrier's parity would be ambiguous
@@ -108,7 +109,7 @@ DL_DEVINL float t3_ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int HD, bool CAUSAL, bool PACKED, bool EXP_POLY>
+template <int HD, bool CAUSAL, bool PACKED, bool EXP_POLY, bool STAGGER>
 __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
     const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
     const __grid_constant__ CUtensorMap tmap_v, bf16* __restrict__ out, int64_t o_tok_stride,
@@ -147,10 +148,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
     for (int s = 0; s < 2; ++s) {
       mbar_init(&S.k_full[s], 1);
       mbar_init(&S.v_full[s], 1);
-      mbar_init(&S.k_empty[s], 1);
-      mbar_init(&S.v_empty[s], 1);
       for (int u = 0; u < 2; ++u) {
         mbar_init(&S.o_done[s][u], 1);
+        mbar_init(&S.k_empty[s][u], 1);
+        mbar_init(&S.v_empty[s][u], 1);
         mbar_init(&S.s_full[s][u], 1);
         mbar_init(&S.p_full[s][u], 128);
       }
@@ -163,9 +164,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
 
+  // 128-key K/V tiles each group touches (causal: group A stops one tile earlier than B at most)
+  const int n_ta = (n_a + 1) >> 1, n_tb = (n_b + 1) >> 1;
   if (warp == 0) {
     // ------------------------------- Q + K producer -------------------------------
-    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
+    if (elect_one()) {  // converged warp + elect.sync keeps the UTMALDG issue on the uniform datapath
       mbar_expect_tx(&S.q_full, (b_active ? 2 : 1) * TILE_BYTES);
 #pragma unroll
       for (int x = 0; x < NBOX; ++x) {
@@ -174,7 +177,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
       }
       for (int t = 0; t < n_t; ++t) {
         const int s = t & 1;
-        mbar_wait(&S.k_empty[s], ((t >> 1) & 1) ^ 1);
+        if (t >= 2) {  // stage s still holds tile t-2: wait until every group that read it has released it
+          if (t - 2 < n_ta) mbar_wait(&S.k_empty[0][s], ((t - 2) >> 1) & 1);
+          if (t - 2 < n_tb) mbar_wait(&S.k_empty[1][s], ((t - 2) >> 1) & 1);
+        }
         mbar_expect_tx(&S.k_full[s], TILE_BYTES);
 #pragma unroll
         for (int x = 0; x < NBOX; ++x) tma_load_2d(S.k[s] + x * 16384, &tmap_k, kv_col0 + x * 64, kv_row0 + t * 128, &S.k_full[s]);
@@ -182,36 +188,47 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
     }
   } else if (warp == 10) {
     // ------------------------------- V producer -------------------------------
-    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
+    if (elect_one()) {
       for (int t = 0; t < n_t; ++t) {
         const int s = t & 1;
-        mbar_wait(&S.v_empty[s], ((t >> 1) & 1) ^ 1);
+        if (t >= 2) {
+          if (t - 2 < n_ta) mbar_wait(&S.v_empty[0][s], ((t - 2) >> 1) & 1);
+          if (t - 2 < n_tb) mbar_wait(&S.v_empty[1][s], ((t - 2) >> 1) & 1);
+        }
         mbar_expect_tx(&S.v_full[s], TILE_BYTES);
 #pragma unroll
         for (int x = 0; x < NBOX; ++x) tma_load_2d(S.v[s] + x * 16384, &tmap_v, kv_col0 + x * 64, kv_row0 + t * 128, &S.v_full[s]);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------- MMA issuer -------------------------------
-    if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA/UTMALDG issue on the uniform datapath
+  } else if (warp == 1 || warp == 11) {
+    // ------------------------------- MMA issuers: warp 1 -> group A, warp 11 -> group B -------------------------------
+    // One issuing thread per group: neither group's MMAs ever queue behind a wait for the other group's P.
+    const int g = warp == 1 ? 0 : 1;
+    const int n_g = g == 0 ? n_a : n_b;
+    if (n_g > 0 && elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA issue on the uniform datapath
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, HD, 0, 1);  // N = head_dim; B (= V) MN-major
-      // S(g, j) = Q_g . K[64 keys of half j]^T  ->  S buffer j & 1 of group g
-      auto issue_s = [&](int g, int j) {
+      const uint32_t qa = smem_u32(S.q[g]);
+      const uint32_t ts = tmem + (uint32_t)g * 128, to = tmem + O_COL + (uint32_t)g * HD;
+      // a 128-key stage is released once per group, behind the last MMA of the group that reads it
+      auto last_half_of_tile = [&](int j) { return (j & 1) || j == n_g - 1; };
+      // S(j) = Q_g . K[64 keys of half j]^T  ->  S buffer j & 1
+      auto issue_s = [&](int j) {
         const int t = j >> 1, s = t & 1;
         mbar_wait(&S.k_full[s], (t >> 1) & 1);
         tc_fence_after();
-        const uint32_t qa = smem_u32(S.q[g]), ka = smem_u32(S.k[s]) + (uint32_t)(j & 1) * 8192u;  // rows 64.. of each box
+        const uint32_t ka = smem_u32(S.k[s]) + (uint32_t)(j & 1) * 8192u;  // rows 64.. of each box
 #pragma unroll
         for (int kk = 0; kk < KSTEPS; ++kk) {
           const uint32_t o = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_bf16_ss(tmem + (uint32_t)g * 128 + (uint32_t)(j & 1) * 64, umma_desc_kmajor_sw128(qa + o),
-                       umma_desc_kmajor_sw128(ka + o), IDESC_QK, kk > 0 ? 1u : 0u);
+          umma_bf16_ss(ts + (uint32_t)(j & 1) * 64, umma_desc_kmajor_sw128(qa + o), umma_desc_kmajor_sw128(ka + o), IDESC_QK,
+                       kk > 0 ? 1u : 0u);
         }
         umma_commit(&S.s_full[g][j & 1]);
+        if (last_half_of_tile(j)) umma_commit(&S.k_empty[g][s]);
       };
-      // O_g += P(g, j) . V[64 keys of half j]
-      auto issue_pv = [&](int g, int j) {
+      // O_g += P(j) . V[64 keys of half j]
+      auto issue_pv = [&](int j) {
         const int t = j >> 1, s = t & 1;
         mbar_wait(&S.p_full[g][j & 1], (j >> 1) & 1);
         mbar_wait(&S.v_full[s], (t >> 1) & 1);
@@ -219,32 +236,24 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
         const uint32_t va = smem_u32(S.v[s]) + (uint32_t)(j & 1) * 8192u;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)  // 16 keys per MMA = 8 packed P columns and 2 KB of V rows
-          t3_umma_ts(tmem + O_COL + (uint32_t)g * HD, tmem + (uint32_t)g * 128 + (uint32_t)(j & 1) * 64 + kk * 8,
-                     t3_desc_mn_sw128(va + kk * 2048, 16384), IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+          t3_umma_ts(to, ts + (uint32_t)(j & 1) * 64 + kk * 8, t3_desc_mn_sw128(va + kk * 2048, 16384), IDESC_PV,
+                     (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&S.o_done[g][j & 1]);
+        if (last_half_of_tile(j)) umma_commit(&S.v_empty[g][s]);
       };
-      // a 128-key stage is released once, after the last MMA that reads its last needed half has been issued
-      auto last_half_of_tile = [&](int j) { return (j & 1) || j == n_h - 1; };
       mbar_wait(&S.q_full, 0);
-      for (int j = 0; j < 2 && j < n_h; ++j) {
-        if (j < n_a) issue_s(0, j);
-        T3_STAMP(12, j * 2);
-        if (j < n_b) issue_s(1, j);
-        T3_STAMP(12, j * 2 + 1);
-        if (last_half_of_tile(j)) umma_commit(&S.k_empty[0]);
-      }
-      for (int j = 0; j < n_h; ++j) {
-        const int j2 = j + 2;
-        if (j < n_a) issue_pv(0, j);
-        T3_STAMP(8, j);
-        if (j2 < n_a) issue_s(0, j2);
-        T3_STAMP(9, j);
-        if (j < n_b) issue_pv(1, j);
-        T3_STAMP(10, j);
-        if (last_half_of_tile(j)) umma_commit(&S.v_empty[(j >> 1) & 1]);
-        if (j2 < n_b) issue_s(1, j2);
-        T3_STAMP(11, j);
-        if (j2 < n_h && last_half_of_tile(j2)) umma_commit(&S.k_empty[(j2 >> 1) & 1]);
+      // Anti-phase start: group B begins one softmax pass after group A.  Both groups share the four SFUs; started together
+      // they stay in lockstep (tcgen05.ld, max, exp2, tcgen05.st phases coincide and the exp2 phases halve each other's
+      // rate), started half a period apart one group's TMEM traffic and dependent chains hide under the other's exp2.
+      if (STAGGER && g == 1) mbar_wait(&S.p_full[0][0], 0);
+      issue_s(0);
+      if (n_g > 1) issue_s(1);
+      T3_STAMP(12, g);
+      for (int j = 0; j < n_g; ++j) {
+        issue_pv(j);
+        T3_STAMP(8 + 2 * g, j);
+        if (j + 2 < n_g) issue_s(j + 2);
+        T3_STAMP(9 + 2 * g, j);
       }
     }
   } else {
@@ -271,17 +280,19 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
         tmem_ld_wait();
         if (r == 0) T3_STAMP(g * 4 + 1, j);
         const int kbase = j * 64;
-        float mx = -INFINITY;
         if (kbase + 63 > key_lim) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e) {
+          for (int e = 0; e < 64; ++e)
             if (kbase + e > key_lim) v[e] = 0xff800000u;  // -inf
-            mx = fmaxf(mx, __uint_as_float(v[e]));
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
         }
+        // four independent max chains (a single fmaxf chain is 32 dependent FMNMX3 with nothing to overlap them)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int e = 0; e < 64; e += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(v[e + u]));
+        }
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         mx *= scale_log2;
         float alpha = 1.f;
         bool rescale = false;
@@ -293,19 +304,22 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
           rescale = true;
         }
         float ls0 = 0.f, ls1 = 0.f;
-        uint32_t pk[32];
 #pragma unroll
-        for (int e = 0; e < 64; e += 2) {
-          const float x0 = fmaf(__uint_as_float(v[e]), scale_log2, -m_ref);
-          const float x1 = fmaf(__uint_as_float(v[e + 1]), scale_log2, -m_ref);
-          const float p0 = (EXP_POLY && (e & 6) == 0) ? t3_ex2_poly(x0) : t3_ex2(x0);  // elements 0 of every 8 ...
-          const float p1 = (EXP_POLY && (e & 6) == 4) ? t3_ex2_poly(x1) : t3_ex2(x1);  // ... and 5 of every 8: 1 in 4
-          ls0 += p0;
-          ls1 += p1;
-          __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-          pk[e >> 1] = *reinterpret_cast<uint32_t*>(&t);
-        }
-        t3_tmem_st_x32(tsj, pk);  // P overwrites the S columns this thread has already read
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = hh * 32; e < hh * 32 + 32; e += 2) {
+            const float x0 = fmaf(__uint_as_float(v[e]), scale_log2, -m_ref);
+            const float x1 = fmaf(__uint_as_float(v[e + 1]), scale_log2, -m_ref);
+            const float p0 = (EXP_POLY && (e & 6) == 0) ? t3_ex2_poly(x0) : t3_ex2(x0);  // elements 0 of every 8 ...
+            const float p1 = (EXP_POLY && (e & 6) == 4) ? t3_ex2_poly(x1) : t3_ex2(x1);  // ... and 5 of every 8: 1 in 4
+            ls0 += p0;
+            ls1 += p1;
+            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+            pk[(e >> 1) & 15] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          tmem_st_32x32b_x16(tsj + hh * 16, pk);  // P overwrites S columns this thread has already read; the first store
+        }                                         // drains while the second 32 exponentials are evaluated
         l_run = l_run * alpha + (ls0 + ls1);
         if (j > 0 && __any_sync(0xffffffffu, rescale)) {
           // rare: bring O to the new reference max before PV_j accumulates onto it
@@ -354,25 +368,25 @@ __global__ void __launch_bounds__(T3_THREADS, 1) attn_prefill_tc3_kernel(
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-template <int HD, bool CAUSAL, bool PACKED, bool EXP_POLY>
+template <int HD, bool CAUSAL, bool PACKED, bool EXP_POLY, bool STAGGER>
 static int launch_t3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, bf16* out, int64_t o_tok_stride,
                      const int32_t* cu_q, const int32_t* kv_past, int B, int heads, int cap, int max_q_len, float scale,
                      cudaStream_t stream) {
   const int smem = (int)sizeof(T3Smem<HD>) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc3_kernel<HD, CAUSAL, PACKED, EXP_POLY>,
+    cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc3_kernel<HD, CAUSAL, PACKED, EXP_POLY, STAGGER>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return dl_set_error((int)e, "dl_attn_tc3(smem attr)");
     attr_set = true;
   }
   dim3 grid((max_q_len + 255) / 256, heads, B);
-  attn_prefill_tc3_kernel<HD, CAUSAL, PACKED, EXP_POLY><<<grid, T3_THREADS, smem, stream>>>(
+  attn_prefill_tc3_kernel<HD, CAUSAL, PACKED, EXP_POLY, STAGGER><<<grid, T3_THREADS, smem, stream>>>(
       tq, tk, tv, out, o_tok_stride, cu_q, kv_past, heads, cap, scale * 1.4426950408889634f);
   DL_CHECK_LAUNCH("dl_attn_tc3");
 }
 
-// flags bit 0: evaluate one exp2 in four with the FMA-pipe polynomial
+// flags bit 0: evaluate one exp2 in four with the FMA-pipe polynomial; bit 1: start both groups together (no anti-phase)
 extern "C" int dl_attn_prefill_tc3(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
                                    int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
                                    int cap, int max_q_len, float scale, int flags, cudaStream_t stream) {
@@ -384,9 +398,14 @@ extern "C" int dl_attn_prefill_tc3(const void* q, int64_t q_tok_stride, const vo
   if (rc) return rc;
   rc = dl_make_tmap_2d(&tv, v_arena, (uint64_t)B * heads * cap, 128, 128, 128, 64);
   if (rc) return rc;
-  if (flags & 1)
-    return launch_t3<128, true, false, true>(tq, tk, tv, (bf16*)out, o_tok_stride, cu_q, kv_past, B, heads, cap, max_q_len, scale, stream);
-  return launch_t3<128, true, false, false>(tq, tk, tv, (bf16*)out, o_tok_stride, cu_q, kv_past, B, heads, cap, max_q_len, scale, stream);
+#define T3_GO(P, G) launch_t3<128, true, false, P, G>(tq, tk, tv, (bf16*)out, o_tok_stride, cu_q, kv_past, B, heads, cap, max_q_len, scale, stream)
+  switch (flags & 3) {
+    case 0: return T3_GO(false, true);
+    case 1: return T3_GO(true, true);
+    case 2: return T3_GO(false, false);
+    default: return T3_GO(true, false);
+  }
+#undef T3_GO
 }
 
 // K6/K7: non-causal attention over a fused projection qkv [n_tok, 3*heads*64] = [q | k | v] (HF CLIPAttention;
@@ -404,7 +423,12 @@ extern "C" int dl_attn_packed_tc3(const void* qkv, void* out, const int32_t* cu_
   if (rc) return rc;
   rc = dl_make_tmap_2d(&tv, base + 2 * C, (uint64_t)n_tok, (uint64_t)C, (uint64_t)(3 * C), 128, 64);
   if (rc) return rc;
-  if (flags & 1)
-    return launch_t3<64, false, true, true>(tq, tk, tv, (bf16*)out, C, cu_q, nullptr, B, heads, 0, max_q_len, scale, stream);
-  return launch_t3<64, false, true, false>(tq, tk, tv, (bf16*)out, C, cu_q, nullptr, B, heads, 0, max_q_len, scale, stream);
+#define T3_GO(P, G) launch_t3<64, false, true, P, G>(tq, tk, tv, (bf16*)out, C, cu_q, nullptr, B, heads, 0, max_q_len, scale, stream)
+  switch (flags & 3) {
+    case 0: return T3_GO(false, true);
+    case 1: return T3_GO(true, true);
+    case 2: return T3_GO(false, false);
+    default: return T3_GO(true, false);
+  }
+#undef T3_GO
 }

@@ -115,7 +115,7 @@ def bench_attn_prefill(out):
         ms_tc2 = timeit(lambda i: L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, ST()), 1)
         diff2 = (o.float() - o_tc.float()).abs().max().item()
         t3 = {}
-        for fl in (0, 1):
+        for fl in (0, 1, 2, 3):
             ms3 = timeit(lambda i: L.attn_prefill_tc3(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, fl, ST()), 1)
             t3[f"tc3_f{fl}_us"] = ms3 * 1e3
             t3[f"tc3_f{fl}_TFLOPs"] = flop / ms3 / 1e9
@@ -144,7 +144,7 @@ def bench_attn_prefill(out):
         ms_tc = timeit(lambda i: L.attn_packed_tc(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, ST()), 1)
         o1 = o.clone()
         t3 = {}
-        for fl in (0, 1):
+        for fl in (0, 1, 2, 3):
             ms3 = timeit(lambda i: L.attn_packed_tc3(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, fl, ST()), 1)
             t3[f"tc3_f{fl}_us"] = ms3 * 1e3
             t3[f"tc3_f{fl}_TFLOPs"] = flop / ms3 / 1e9

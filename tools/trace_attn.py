@@ -41,7 +41,7 @@ def main():
     cu = torch.arange(0, (B + 1) * Lq, Lq, device="cuda", dtype=torch.int32)
     past = torch.zeros(B, device="cuda", dtype=torch.int32)
     res = {}
-    for flags in (0, 1):
+    for flags in (0, 1, 2):
         tr = torch.zeros(16 * 64, device="cuda", dtype=torch.int64)
         assert dll.dl_debug_t3_set_trace(P(tr)) == 0
         fn = dll.dl_attn_prefill_tc3
