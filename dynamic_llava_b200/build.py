@@ -26,6 +26,7 @@ SOURCES = [
     "attn_prefill_tc.cu",
     "attn_prefill_tc2.cu",
     "attn_prefill_tc3.cu",
+    "attn_prefill_tc4.cu",
     "skinny_gemm.cu",
     "gemm_tc.cu",
     "decode_fused.cu",

@@ -147,6 +147,15 @@ int dl_attn_prefill_tc3(const void* q, int64_t q_tok_stride, const void* k_arena
 int dl_attn_packed_tc3(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
                        int max_q_len, float scale, int flags, cudaStream_t stream);
 
+/* K2 v4 / K6-K7 v4: v3's pipeline in a persistent kernel (grid = #SMs, heaviest-first tile list, barriers indexed by running
+ * counters so that loads, S(0)/S(1) and the TMEM allocation of the next tile hide under the current tile's tail;
+ * attn_prefill_tc4.cu).  flags bit 0 as for v3. */
+int dl_attn_prefill_tc4(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
+                        int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
+                        int cap, int max_q_len, float scale, int flags, cudaStream_t stream);
+int dl_attn_packed_tc4(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
+                       int max_q_len, float scale, int flags, cudaStream_t stream);
+
 /* ---- decode-step weight streaming: every nn.Linear at q_len == 1 (DML:1011-1013, :1127, :328, :2709) ----------- */
 /* partial fp32 [splits, M, N] = per-split X[M,K] . W[N,K]^T; M <= 64, K % 64 == 0.  TMA + tcgen05.
  * l2_prefetch_mb: bytes of W (total over the grid) each launch asks the TMA unit to pull into L2 ahead of its smem ring

@@ -115,12 +115,13 @@ def bench_attn_prefill(out):
         ms_tc2 = timeit(lambda i: L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, ST()), 1)
         diff2 = (o.float() - o_tc.float()).abs().max().item()
         t3 = {}
-        for fl in (0, 1, 2, 3):
-            ms3 = timeit(lambda i: L.attn_prefill_tc3(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, fl, ST()), 1)
-            t3[f"tc3_f{fl}_us"] = ms3 * 1e3
-            t3[f"tc3_f{fl}_TFLOPs"] = flop / ms3 / 1e9
-            t3[f"tc3_f{fl}_frac_of_sustained_bf16"] = flop / ms3 / 1e9 / pk["bf16_tflops_sustained"]
-            t3[f"tc3_f{fl}_vs_tc_maxdiff"] = (o.float() - o_tc.float()).abs().max().item()
+        for fl in (0, 1):
+            for nm, fn3 in (("tc3", L.attn_prefill_tc3), ("tc4", L.attn_prefill_tc4)):
+                ms3 = timeit(lambda i: fn3(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, fl, ST()), 1)
+                t3[f"{nm}_f{fl}_us"] = ms3 * 1e3
+                t3[f"{nm}_f{fl}_TFLOPs"] = flop / ms3 / 1e9
+                t3[f"{nm}_f{fl}_frac_of_sustained_bf16"] = flop / ms3 / 1e9 / pk["bf16_tflops_sustained"]
+                t3[f"{nm}_f{fl}_vs_tc_maxdiff"] = (o.float() - o_tc.float()).abs().max().item()
         ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * H, hd, P(K), P(V), nh * cap * hd, cap * hd, hd, 0, P(o), H, P(cu), P(past), B, nh, hd, Lq, 1, sc, ST()), 1)
         diff = (o.float() - o_tc.float()).abs().max().item()
         q4 = qkv[:, :H].view(B, Lq, nh, hd).transpose(1, 2)
@@ -144,11 +145,12 @@ def bench_attn_prefill(out):
         ms_tc = timeit(lambda i: L.attn_packed_tc(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, ST()), 1)
         o1 = o.clone()
         t3 = {}
-        for fl in (0, 1, 2, 3):
-            ms3 = timeit(lambda i: L.attn_packed_tc3(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, fl, ST()), 1)
-            t3[f"tc3_f{fl}_us"] = ms3 * 1e3
-            t3[f"tc3_f{fl}_TFLOPs"] = flop / ms3 / 1e9
-            t3[f"tc3_f{fl}_vs_tc2_maxdiff"] = (o.float() - o1.float()).abs().max().item()
+        for fl in (0, 1):
+            for nm, fn3 in (("tc3", L.attn_packed_tc3), ("tc4", L.attn_packed_tc4)):
+                ms3 = timeit(lambda i: fn3(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, fl, ST()), 1)
+                t3[f"{nm}_f{fl}_us"] = ms3 * 1e3
+                t3[f"{nm}_f{fl}_TFLOPs"] = flop / ms3 / 1e9
+                t3[f"{nm}_f{fl}_vs_tc2_maxdiff"] = (o.float() - o1.float()).abs().max().item()
         kp = ctypes.c_void_p(qkv.data_ptr() + C * 2)
         vp = ctypes.c_void_p(qkv.data_ptr() + 2 * C * 2)
         ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * C, hd, kp, vp, 0, hd, 3 * C, 1, P(o), C, P(cu), None, B, nh, hd, N, 0, sc, ST()), 1)
