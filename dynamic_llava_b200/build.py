@@ -23,9 +23,7 @@ SOURCES = [
     "rope_append.cu",
     "attn_decode.cu",
     "attn_prefill_mma.cu",
-    "attn_prefill_tc.cu",
     "attn_prefill_tc2.cu",
-    "attn_prefill_tc3.cu",
     "attn_prefill_tc4.cu",
     "skinny_gemm.cu",
     "gemm_tc.cu",

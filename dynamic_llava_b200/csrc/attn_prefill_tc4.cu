@@ -19,7 +19,7 @@
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
 
-#define T4_THREADS 384
+#define T4_THREADS 352
 
 #ifdef DL_T4_TRACE
 // debug build only (tools/trace_attn.py --tc4): per-item clock stamps of CTA 0: slot = group * 4 + kind, index = item ordinal
@@ -43,8 +43,8 @@ struct T4Smem {
   alignas(1024) uint8_t k[2][TILE];
   alignas(1024) uint8_t v[2][TILE];
   alignas(1024) uint8_t ostage[8][4096];  // per softmax warp: 32 rows x 64 bf16 of O, 128B-swizzled, source of the TMA store
-  alignas(8) uint64_t q_full;
-  alignas(8) uint64_t q_empty;        // count 2: one tcgen05.commit per issuer behind its last S of the item
+  alignas(8) uint64_t q_full[2];      // per group: the groups drift apart by the causal imbalance (two halves per item)
+  alignas(8) uint64_t q_empty[2];     // tcgen05.commit of the group's issuer behind its last S of the item
   alignas(8) uint64_t k_full[2];
   alignas(8) uint64_t v_full[2];
   alignas(8) uint64_t k_empty[2][2];  // [group][stage]
@@ -54,6 +54,8 @@ struct T4Smem {
   alignas(8) uint64_t o_done[2][2];
   alignas(8) uint64_t o_free[2];      // count 128: the group's softmax threads have read O out of TMEM
   uint32_t tmem_base;
+  int32_t cu_s[64];                   // CSR header and past lengths of up to 63 samples: every role re-derives every item, and
+  int32_t past_s[64];                 // two dependent global loads per item per role were ~1 k cycles at each item boundary
 };
 
 DL_DEVINL uint64_t t4_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -117,14 +119,42 @@ struct T4Item {
   int h, q_start, q_len, m0, off, kv_total, n_a, n_b, n_h, n_t, n_ta, n_tb, kv_row0, kv_col0;
   bool b_active;
 };
-template <int HD, bool CAUSAL, bool PACKED>
-DL_DEVINL bool t4_item(int w, int n_qblk, int heads, int Bn, int cap, const int32_t* __restrict__ cu_q,
-                       const int32_t* __restrict__ kv_past, T4Item& I) {
+// position in the item list w -> (query block, sample, head), advanced by gridDim.x without divisions
+struct T4Pos {
+  int w, blk, b, h;      // w = (blk * Bn + b) * heads + h
+  int dw, dblk, db, dh;  // the same decomposition of the stride gridDim.x
+};
+DL_DEVINL void t4_pos_init(T4Pos& p, int w0, int stride, int heads, int Bn) {
   const int per = heads * Bn;
-  const int mt = n_qblk - 1 - w / per;  // heaviest causal blocks first
-  const int rem = w % per;
-  const int b = rem / heads;
-  I.h = rem % heads;
+  p.w = w0;
+  p.blk = w0 / per;
+  p.b = (w0 % per) / heads;
+  p.h = w0 % heads;
+  p.dw = stride;
+  p.dblk = stride / per;
+  p.db = (stride % per) / heads;
+  p.dh = stride % heads;
+}
+DL_DEVINL void t4_pos_next(T4Pos& p, int heads, int Bn) {
+  p.w += p.dw;
+  p.h += p.dh;
+  p.b += p.db;
+  p.blk += p.dblk;
+  if (p.h >= heads) {
+    p.h -= heads;
+    ++p.b;
+  }
+  if (p.b >= Bn) {
+    p.b -= Bn;
+    ++p.blk;
+  }
+}
+template <int HD, bool CAUSAL, bool PACKED>
+DL_DEVINL bool t4_item(const T4Pos& p, int n_qblk, int heads, int cap, const int32_t* __restrict__ cu_q,
+                       const int32_t* __restrict__ kv_past, T4Item& I) {
+  const int mt = n_qblk - 1 - p.blk;  // heaviest causal blocks first
+  const int b = p.b;
+  I.h = p.h;
   I.q_start = cu_q[b];
   I.q_len = cu_q[b + 1] - I.q_start;
   I.m0 = mt * 256;
@@ -163,9 +193,9 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_o);
-    mbar_init(&S.q_full, 1);
-    mbar_init(&S.q_empty, 2);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&S.q_full[s], 1);
+      mbar_init(&S.q_empty[s], 1);
       mbar_init(&S.k_full[s], 1);
       mbar_init(&S.v_full[s], 1);
       mbar_init(&S.o_free[s], 128);
@@ -180,26 +210,38 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&S.tmem_base);
+  const bool hdr_in_smem = Bn < 64;
+  if (hdr_in_smem && threadIdx.x >= 64 && threadIdx.x < 64 + 64) {
+    const int i = threadIdx.x - 64;
+    if (i <= Bn) S.cu_s[i] = cu_q[i];
+    S.past_s[i] = (kv_past != nullptr && i < Bn) ? kv_past[i] : 0;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
+  if (hdr_in_smem) {
+    cu_q = S.cu_s;
+    kv_past = S.past_s;
+  }
   T4Item I;
+  T4Pos pos;
 
   if (warp == 0) {
-    // ------------------------------- Q + K producer -------------------------------
-    if (elect_one()) {  // converged warp + elect.sync keeps the UTMALDG issue on the uniform datapath
-      int it = 0, T = 0;  // items and 128-key tiles loaded so far
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        if (!t4_item<HD, CAUSAL, PACKED>(w, n_qblk, heads, Bn, cap, cu_q, kv_past, I)) continue;
-        if (it >= 1) mbar_wait(&S.q_empty, (it - 1) & 1);  // both groups have issued (and finished) their last S of the previous item
-        mbar_expect_tx(&S.q_full, (I.b_active ? 2 : 1) * TILE_BYTES);
+    if (lane == 0) {
+      // ------------------------------- Q + K producer -------------------------------
+      int T = 0, ia[2] = {0, 0};  // 128-key tiles loaded so far; items each group has worked on
+      for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
+        if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
+        auto load_q = [&](int g) {
+          if (ia[g] >= 1) mbar_wait(&S.q_empty[g], (ia[g] - 1) & 1);  // the group's last S of its previous item has read the tile
+          mbar_expect_tx(&S.q_full[g], TILE_BYTES);
 #pragma unroll
-        for (int x = 0; x < NBOX; ++x) {
-          tma_load_2d(S.q[0] + x * 16384, &tmap_q, I.h * HD + x * 64, I.q_start + I.m0, &S.q_full);
-          if (I.b_active) tma_load_2d(S.q[1] + x * 16384, &tmap_q, I.h * HD + x * 64, I.q_start + I.m0 + 128, &S.q_full);
-        }
-        for (int t = 0; t < I.n_t; ++t, ++T) {
+          for (int x = 0; x < NBOX; ++x)
+            tma_load_2d(S.q[g] + x * 16384, &tmap_q, I.h * HD + x * 64, I.q_start + I.m0 + g * 128, &S.q_full[g]);
+          ++ia[g];
+        };
+        auto load_k = [&](int t) {
           const int s = T & 1;
           if (T >= 2) {  // stage s still holds tile T-2: both groups release every tile
             mbar_wait(&S.k_empty[0][s], ((T >> 1) & 1) ^ 1);
@@ -209,16 +251,19 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
 #pragma unroll
           for (int x = 0; x < NBOX; ++x)
             tma_load_2d(S.k[s] + x * 16384, &tmap_k, I.kv_col0 + x * 64, I.kv_row0 + t * 128, &S.k_full[s]);
-        }
-        ++it;
+          ++T;
+        };
+        // group A finishes an item two halves before group B: give it its Q tile and the first K tile before waiting for B
+        load_q(0);
+        load_k(0);
+        if (I.b_active) load_q(1);
+        for (int t = 1; t < I.n_t; ++t) load_k(t);
       }
-    }
-  } else if (warp == 10) {
-    // ------------------------------- V producer -------------------------------
-    if (elect_one()) {
+    } else if (lane == 1) {
+      // ------------------------------- V producer -------------------------------
       int T = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        if (!t4_item<HD, CAUSAL, PACKED>(w, n_qblk, heads, Bn, cap, cu_q, kv_past, I)) continue;
+      for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
+        if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
         for (int t = 0; t < I.n_t; ++t, ++T) {
           const int s = T & 1;
           if (T >= 2) {
@@ -232,8 +277,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
         }
       }
     }
-  } else if (warp == 1 || warp == 11) {
-    // ------------------------------- MMA issuers: warp 1 -> group A, warp 11 -> group B -------------------------------
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------- MMA issuers: warp 1 -> group A, warp 10 -> group B -------------------------------
     const int g = warp == 1 ? 0 : 1;
     if (elect_one()) {  // converged warp + elect.sync keeps the UTCHMMA issue on the uniform datapath
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 64, 0, 0);
@@ -241,11 +286,11 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
       const uint32_t qa = smem_u32(S.q[g]);
       const uint32_t ts = tmem + (uint32_t)g * 128, to = tmem + O_COL + (uint32_t)g * HD;
       int it = 0, T0 = 0, J = 0, ia = 0;  // items seen, tiles before this item, halves of this group so far, items this group worked on
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        if (!t4_item<HD, CAUSAL, PACKED>(w, n_qblk, heads, Bn, cap, cu_q, kv_past, I)) continue;
+      for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
+        if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
         const int n_g = g == 0 ? I.n_a : I.n_b;
         const int n_tg = g == 0 ? I.n_ta : I.n_tb;
-        mbar_wait(&S.q_full, it & 1);
+        if (n_g > 0) mbar_wait(&S.q_full[g], ia & 1);
         // S(j) = Q_g . K[64 keys of half j]^T  ->  S buffer (J + j) & 1
         auto issue_s = [&](int j) {
           const int T = T0 + (j >> 1), s = T & 1, jj = J + j;
@@ -260,7 +305,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
           }
           umma_commit(&S.s_full[g][jj & 1]);
           if ((j & 1) || j == n_g - 1) umma_commit(&S.k_empty[g][s]);  // last half of this tile the group reads
-          if (j == n_g - 1) umma_commit(&S.q_empty);                   // last read of this item's Q tile
+          if (j == n_g - 1) umma_commit(&S.q_empty[g]);                // last read of this item's Q tile
         };
         // O_g += P(j) . V[64 keys of half j]
         auto issue_pv = [&](int j) {
@@ -291,8 +336,6 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
           }
           J += n_g;
           ++ia;
-        } else {
-          umma_commit(&S.q_empty);
         }
         // tiles of this item the group did not read are released too (behind everything issued so far), so that the
         // per-group empty barriers advance exactly once per tile
@@ -316,8 +359,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
     const uint32_t to = tmem + O_COL + (uint32_t)g * HD + lane_addr;
     int J = 0;
     [[maybe_unused]] int ord = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      if (!t4_item<HD, CAUSAL, PACKED>(w, n_qblk, heads, Bn, cap, cu_q, kv_past, I)) continue;
+    for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
+      if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
       const int n_g = g == 0 ? I.n_a : I.n_b;
       if (n_g == 0) continue;
       if (r == 0) T4_STAMP(g * 4 + 0, ord);  // item entered
@@ -331,6 +374,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
         mbar_wait(&S.s_full[g][jj & 1], (jj >> 1) & 1);
         tc_fence_after();
         if (r == 0 && j == 0) T4_STAMP(g * 4 + 1, ord);  // first S of the item seen
+        // S is read ONCE.  (Issuing the tcgen05.ld of S(j+1) early into registers this half has consumed was measured 4 % slower,
+        // profiles/r1_ncu_attn_prefill_tc4.md: the ~230-cycle load is already hidden by the other group's warp on the same SMSP.)
         uint32_t v[64];
         tmem_ld_32x32b_x32(tsj, v);
         tmem_ld_32x32b_x32(tsj + 32, v + 32);
@@ -420,15 +465,18 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
           mbar_arrive(&S.o_free[g]);
         }
         if (warp_full) {
-          if (lane == 0) t4_bulk_wait_read0();  // the previous box has left the staging tile
-          __syncwarp();
+          bf16x8 pk8[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float f[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(ov[c * 8 + u]) * inv;
-            *reinterpret_cast<bf16x8*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = pack8(f);
+            pk8[c] = pack8(f);
           }
+          if (lane == 0) t4_bulk_wait_read0();  // the previous box has left the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) *reinterpret_cast<bf16x8*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = pk8[c];
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {

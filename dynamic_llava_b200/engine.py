@@ -87,9 +87,9 @@ class Engine:
         if self.dtype != torch.bfloat16:
             raise RuntimeError("kernels compute in bf16: load the model with torch_dtype=torch.bfloat16")
         self.packed = None
-        # "tc3" (default: half tiles, double-buffered S) | "tc2" | "tc" (tcgen05 kernels) | "mma" (warp-MMA tile path)
-        self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc3")
-        self.attn_flags = int(os.environ.get("DLB200_ATTN_FLAGS", "0"))  # dl_attn_prefill_tc3 flags (bit 0: FMA-pipe exp2)
+        # "tc4" (default: persistent tcgen05 kernel) | "tc2" (non-persistent tcgen05) | "mma" (warp-MMA tile path)
+        self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc4")
+        self.attn_flags = int(os.environ.get("DLB200_ATTN_FLAGS", "0"))  # dl_attn_prefill_tc4 flags (bit 0: FMA-pipe exp2)
         self.packed_attn = os.environ.get("DLB200_PACKED_ATTN", "tc")  # CLIP / predictor attention: "tc" (tcgen05) | "mma"
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
@@ -200,8 +200,8 @@ class Engine:
         out = torch.empty(B * N, C, device=qkv.device, dtype=qkv.dtype)
         cu = torch.arange(0, (B + 1) * N, N, device=qkv.device, dtype=torch.int32)
         if hd == 64 and not causal and self.packed_attn == "tc":
-            if self.prefill_attn == "tc3":
-                self.L.attn_packed_tc3(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), self.attn_flags, _stream())
+            if self.prefill_attn == "tc4":
+                self.L.attn_packed_tc4(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), self.attn_flags, _stream())
             else:
                 self.L.attn_packed_tc(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), _stream())
             self.launches += 1
@@ -382,13 +382,11 @@ class Engine:
                            None, None, N, B, nh, hd, cap, _stream())
         attn = torch.empty(N, H, device=x.device, dtype=x.dtype)
         scale = 1.0 / math.sqrt(hd)
-        if self.prefill_attn == "tc3":
-            self.L.attn_prefill_tc3(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, self.attn_flags,
+        if self.prefill_attn == "tc4":
+            self.L.attn_prefill_tc4(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, self.attn_flags,
                                     _stream())
         elif self.prefill_attn == "tc2":
             self.L.attn_prefill_tc2(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())
-        elif self.prefill_attn == "tc":
-            self.L.attn_prefill_tc(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())
         else:
             self.L.attn_varlen(_p(qkv), 3 * H, hd, _p(K), _p(V), nh * cap * hd, cap * hd, hd, 0, _p(attn), H, _p(cu), _p(kvl), B, nh,
                                hd, Lq, 1, scale, _stream())

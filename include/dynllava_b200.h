@@ -122,12 +122,8 @@ int dl_attn_varlen(const void* q, int64_t q_tok_stride, int64_t q_head_stride, c
                    int64_t kv_batch_stride, int64_t kv_head_stride, int64_t kv_tok_stride, int kv_packed, void* out,
                    int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int B, int heads, int head_dim,
                    int max_q_len, int causal, float scale, cudaStream_t stream);
-/* K2 proper: TMA + tcgen05/TMEM causal prefill attention, head_dim 128, K/V in the arena (attn_prefill_tc.cu). */
-int dl_attn_prefill_tc(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
-                       int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
-                       int cap, int max_q_len, float scale, cudaStream_t stream);
-
-/* K2 v2: same contract; 256 query rows per CTA, ping-pong softmax groups, P and O resident in TMEM (attn_prefill_tc2.cu). */
+/* K2 (v2, kept as the simple non-persistent form): TMA + tcgen05/TMEM causal prefill attention, head_dim 128, K/V in the arena;
+ * 256 query rows per CTA, ping-pong softmax groups, P and O resident in TMEM (attn_prefill_tc2.cu). */
 int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
                         int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
                         int cap, int max_q_len, float scale, cudaStream_t stream);
@@ -138,18 +134,10 @@ int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena
 int dl_attn_packed_tc(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
                       int max_q_len, float scale, cudaStream_t stream);
 
-/* K2 v3 / K6-K7 v3: same contracts as dl_attn_prefill_tc2 / dl_attn_packed_tc; 64-key half tiles with double-buffered S in
- * TMEM so that softmax and tensor pipe never wait on each other's latency (attn_prefill_tc3.cu).  flags bit 0: one exp2 in
- * four on the FMA pipe (degree-3 polynomial, rel. error 7.5e-5) instead of the SFU. */
-int dl_attn_prefill_tc3(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
-                        int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
-                        int cap, int max_q_len, float scale, int flags, cudaStream_t stream);
-int dl_attn_packed_tc3(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
-                       int max_q_len, float scale, int flags, cudaStream_t stream);
-
-/* K2 v4 / K6-K7 v4: v3's pipeline in a persistent kernel (grid = #SMs, heaviest-first tile list, barriers indexed by running
- * counters so that loads, S(0)/S(1) and the TMEM allocation of the next tile hide under the current tile's tail;
- * attn_prefill_tc4.cu).  flags bit 0 as for v3. */
+/* K2 v4 / K6-K7 v4 (default): same contracts as dl_attn_prefill_tc2 / dl_attn_packed_tc.  64-key half tiles with double-buffered
+ * S in TMEM, one MMA issuer per softmax group, in a persistent kernel (grid = #SMs, heaviest-first tile list, barriers indexed by
+ * running counters so that the loads and S(0)/S(1) of the next tile hide under the current tile's tail), O written with TMA stores
+ * (attn_prefill_tc4.cu).  flags bit 0: one exp2 in four on the FMA pipe (degree-3 polynomial, rel. error 7.5e-5) instead of the SFU. */
 int dl_attn_prefill_tc4(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
                         int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
                         int cap, int max_q_len, float scale, int flags, cudaStream_t stream);

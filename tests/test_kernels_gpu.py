@@ -439,14 +439,6 @@ def _call_mma(L):
     return fn
 
 
-def _call_tc(L):
-    def fn(qkv, K, V, out, cu, past, N, B, nh, hd, cap, max_q, causal):
-        assert causal and hd == 128
-        H = nh * hd
-        L.attn_prefill_tc(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), N, B, nh, cap, max_q, 1.0 / math.sqrt(hd), ST())
-    return fn
-
-
 @pytest.mark.parametrize("hd,causal,q_lens,pasts", [(128, True, [146, 146], [0, 0]), (128, True, [607, 33, 128], [0, 0, 0]),
                                                     (128, True, [19, 70], [27, 5]), (64, False, [577, 577], [0, 0]),
                                                     (64, False, [17, 16, 1], [0, 0, 0]), (128, False, [100], [0]), (64, True, [65], [0])])
@@ -492,12 +484,6 @@ def test_attn_packed_tcgen05_noncausal_hd64(L, B, N, nh):
             assert (got[sl, h * hd:(h + 1) * hd] - ref).abs().max() < 2e-2, (b, h)
 
 
-@pytest.mark.parametrize("q_lens,pasts", [([128], [0]), ([146, 146], [0, 0]), ([607, 33, 128, 300], [0, 0, 0, 0]), ([19, 70], [27, 5]),
-                                          ([1587], [0])])
-def test_attn_prefill_tcgen05(L, q_lens, pasts):
-    _varlen_case(L, _call_tc(L), 128, True, q_lens, pasts, nh=2)
-
-
 def _call_tc2(L):
     def fn(qkv, K, V, out, cu, past, N, B, nh, hd, cap, max_q, causal):
         assert causal and hd == 128
@@ -532,12 +518,11 @@ def test_attn_prefill_pingpong_rescale_path(L, which):
     assert (out.float().cpu() - ref).abs().max() < 3e-2 * max(1.0, ref.abs().max().item())
 
 
-def _call_tc3(L, flags, impl="tc3"):
+def _call_tc4(L, flags):
     def fn(qkv, K, V, out, cu, past, N, B, nh, hd, cap, max_q, causal):
         assert causal and hd == 128
         H = nh * hd
-        f = L.attn_prefill_tc3 if impl == "tc3" else L.attn_prefill_tc4
-        f(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), N, B, nh, cap, max_q, 1.0 / math.sqrt(hd), flags, ST())
+        L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(out), H, P(cu), P(past), N, B, nh, cap, max_q, 1.0 / math.sqrt(hd), flags, ST())
     return fn
 
 
@@ -545,11 +530,10 @@ def _call_tc3(L, flags, impl="tc3"):
 @pytest.mark.parametrize("q_lens,pasts", [([128], [0]), ([256], [0]), ([1], [0]), ([63, 64, 65], [0, 0, 0]), ([146, 146], [0, 0]),
                                           ([607, 33, 129, 300], [0, 0, 0, 0]), ([19, 70], [27, 5]), ([1587], [0]), ([300], [500]),
                                           ([200, 257], [64, 63])])
-@pytest.mark.parametrize("impl", ["tc3", "tc4"])
-def test_attn_prefill_tcgen05_double_buffered(L, q_lens, pasts, flags, impl):
-    """K2 v3 / v4 (persistent): 64-key half tiles, two S buffers per group; flags=1 evaluates a quarter of the exp2 with the FMA
+def test_attn_prefill_tc4_persistent(L, q_lens, pasts, flags):
+    """K2 v4 (persistent): 64-key half tiles, two S buffers per group; flags=1 evaluates a quarter of the exp2 with the FMA
     polynomial."""
-    _varlen_case(L, _call_tc3(L, flags, impl), 128, True, q_lens, pasts, nh=2)
+    _varlen_case(L, _call_tc4(L, flags), 128, True, q_lens, pasts, nh=2)
 
 
 @pytest.mark.parametrize("flags", [0, 1])
@@ -558,20 +542,19 @@ def test_attn_prefill_tc4_persistent_many_items(L, flags):
     some with an idle group B"""
     q_lens = [300, 1, 129, 256, 700, 64, 513, 90, 257, 128]
     pasts = [0, 40, 3, 0, 0, 200, 0, 70, 0, 1]
-    _varlen_case(L, _call_tc3(L, flags, "tc4"), 128, True, q_lens, pasts, nh=40)
+    _varlen_case(L, _call_tc4(L, flags), 128, True, q_lens, pasts, nh=40)
 
 
 @pytest.mark.parametrize("flags", [0, 1])
 @pytest.mark.parametrize("B,N,nh", [(2, 577, 16), (3, 576, 8), (2, 17, 2), (1, 300, 4), (2, 64, 1), (1, 129, 2)])
-@pytest.mark.parametrize("impl", ["tc3", "tc4"])
-def test_attn_packed_tc3_noncausal_hd64(L, B, N, nh, flags, impl):
-    """CLIP (577 tokens, 16 heads) and predictor (576 tokens, 8 heads) attention on the v3 / v4 pipeline vs fp32 attention."""
+def test_attn_packed_tc4_noncausal_hd64(L, B, N, nh, flags):
+    """CLIP (577 tokens, 16 heads) and predictor (576 tokens, 8 heads) attention on the persistent pipeline vs fp32 attention."""
     hd = 64
     C = nh * hd
     qkv = rnd(B * N, 3 * C, seed=91)
     out = torch.full((B * N, C), float("nan"), device=DEV, dtype=BF)
     cu = torch.arange(0, (B + 1) * N, N, dtype=torch.int32, device=DEV)
-    (L.attn_packed_tc3 if impl == "tc3" else L.attn_packed_tc4)(P(qkv.to(DEV)), P(out), P(cu), B * N, B, nh, hd, N, 1.0 / math.sqrt(hd), flags, ST())
+    L.attn_packed_tc4(P(qkv.to(DEV)), P(out), P(cu), B * N, B, nh, hd, N, 1.0 / math.sqrt(hd), flags, ST())
     torch.cuda.synchronize()
     got = out.float().cpu()
     assert torch.isfinite(got).all()
@@ -582,9 +565,8 @@ def test_attn_packed_tc3_noncausal_hd64(L, B, N, nh, flags, impl):
             assert (got[sl, h * hd:(h + 1) * hd] - ref).abs().max() < 2e-2, (b, h)
 
 
-@pytest.mark.parametrize("impl", ["tc3", "tc4"])
 @pytest.mark.parametrize("flags", [0, 1])
-def test_attn_prefill_tc3_rescale_path(L, flags, impl):
+def test_attn_prefill_tc4_rescale_path(L, flags):
     """keys whose scores grow by far more than 2^8 along the sequence force the lazy O-rescale branch"""
     B, nh, hd, Lq = 1, 1, 128, 512
     H = nh * hd
@@ -596,7 +578,7 @@ def test_attn_prefill_tc3_rescale_path(L, flags, impl):
     out = torch.zeros(Lq, H, device=DEV, dtype=BF)
     cu = torch.tensor([0, Lq], dtype=torch.int32, device=DEV)
     past = torch.zeros(1, dtype=torch.int32, device=DEV)
-    (L.attn_prefill_tc3 if impl == "tc3" else L.attn_prefill_tc4)(P(qkv.to(DEV)), 3 * H, P(K.to(DEV)), P(V.to(DEV)), P(out), H, P(cu), P(past), Lq,
+    L.attn_prefill_tc4(P(qkv.to(DEV)), 3 * H, P(K.to(DEV)), P(V.to(DEV)), P(out), H, P(cu), P(past), Lq,
                                                                    B, nh, Lq + 4, Lq, 1.0 / math.sqrt(hd), flags, ST())
     torch.cuda.synchronize()
     ref = _sdpa_ref(qkv[:, :hd], K[0, 0, :Lq], V[0, 0, :Lq], causal_off=0)
