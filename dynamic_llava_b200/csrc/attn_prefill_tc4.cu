@@ -119,40 +119,53 @@ struct T4Item {
   int h, q_start, q_len, m0, off, kv_total, n_a, n_b, n_h, n_t, n_ta, n_tb, kv_row0, kv_col0;
   bool b_active;
 };
-// position in the item list w -> (query block, sample, head), advanced by gridDim.x without divisions
+// Item schedule.  The (sample, head) pairs are taken in WINDOWS of Wn = 2*gridDim.x / n_qblk pairs (their K/V, Wn * 2 * len * HD * 2
+// bytes, stay in the 126 MB L2 while all their query blocks are processed: a globally heaviest-first list re-read K/V from HBM
+// 3x, profiles/r1_ncu_attn_prefill_tc4.md).  Inside a window the items are sorted heaviest block first and dealt out in a snake:
+// CTA c takes positions c, 2G-1-c, 2G+c, ...; with two items per CTA the pair is (block n-1-i, block i): equal causal work.
 struct T4Pos {
-  int w, blk, b, h;      // w = (blk * Bn + b) * heads + h
-  int dw, dblk, db, dh;  // the same decomposition of the stride gridDim.x
+  int step, n_steps;  // step = window * slots_per_window + slot
+  int wnd, slot;      // tracked incrementally (no division per step)
+  int Wn, spw, HB;    // pairs per window, slots per window, heads * samples
+  float inv_heads;
+  int blk, b, h;      // decoded item: query block rank (0 = heaviest), sample, head
 };
-DL_DEVINL void t4_pos_init(T4Pos& p, int w0, int stride, int heads, int Bn) {
-  const int per = heads * Bn;
-  p.w = w0;
-  p.blk = w0 / per;
-  p.b = (w0 % per) / heads;
-  p.h = w0 % heads;
-  p.dw = stride;
-  p.dblk = stride / per;
-  p.db = (stride % per) / heads;
-  p.dh = stride % heads;
+// floor(a / d) for 0 <= a < 2^22, d > 0 through the float reciprocal (exact: (a + 0.5) / d is >= 0.5 / d away from an integer)
+DL_DEVINL int t4_div(int a, float inv_d) { return (int)(((float)a + 0.5f) * inv_d); }
+DL_DEVINL void t4_pos_init(T4Pos& p, int heads, int Bn, int n_qblk) {
+  const int G = gridDim.x;
+  p.HB = heads * Bn;
+  p.Wn = max(1, min(p.HB, (2 * G) / n_qblk));
+  p.spw = (p.Wn * n_qblk + G - 1) / G;
+  p.n_steps = ((p.HB + p.Wn - 1) / p.Wn) * p.spw;
+  p.step = p.wnd = p.slot = 0;
+  p.inv_heads = 1.0f / (float)heads;
 }
-DL_DEVINL void t4_pos_next(T4Pos& p, int heads, int Bn) {
-  p.w += p.dw;
-  p.h += p.dh;
-  p.b += p.db;
-  p.blk += p.dblk;
-  if (p.h >= heads) {
-    p.h -= heads;
-    ++p.b;
+DL_DEVINL void t4_pos_next(T4Pos& p) {
+  ++p.step;
+  if (++p.slot == p.spw) {
+    p.slot = 0;
+    ++p.wnd;
   }
-  if (p.b >= Bn) {
-    p.b -= Bn;
-    ++p.blk;
-  }
+}
+// decode the current step for this CTA; false = no item in this slot
+DL_DEVINL bool t4_pos_decode(T4Pos& p, int heads, int n_qblk) {
+  const int G = gridDim.x, c = blockIdx.x;
+  const int hb0 = p.wnd * p.Wn;
+  const int wn = min(p.Wn, p.HB - hb0);  // pairs in this window
+  const int pos = (p.slot & 1) ? (p.slot + 1) * G - 1 - c : p.slot * G + c;
+  if (pos >= wn * n_qblk) return false;
+  p.blk = t4_div(pos, 1.0f / (float)wn);
+  const int hb = hb0 + (pos - p.blk * wn);
+  p.b = t4_div(hb, p.inv_heads);
+  p.h = hb - p.b * heads;
+  return true;
 }
 template <int HD, bool CAUSAL, bool PACKED>
 DL_DEVINL bool t4_item(const T4Pos& p, int n_qblk, int heads, int cap, const int32_t* __restrict__ cu_q,
                        const int32_t* __restrict__ kv_past, T4Item& I) {
-  const int mt = n_qblk - 1 - p.blk;  // heaviest causal blocks first
+  // rank 0 = the heaviest block: the last one when causal, any full one otherwise (the ragged last block is the lightest)
+  const int mt = CAUSAL ? n_qblk - 1 - p.blk : p.blk;
   const int b = p.b;
   I.h = p.h;
   I.q_start = cu_q[b];
@@ -231,8 +244,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
     if (lane == 0) {
       // ------------------------------- Q + K producer -------------------------------
       int T = 0, ia[2] = {0, 0};  // 128-key tiles loaded so far; items each group has worked on
-      for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
-        if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
+      for (t4_pos_init(pos, heads, Bn, n_qblk); pos.step < pos.n_steps; t4_pos_next(pos)) {
+        if (!t4_pos_decode(pos, heads, n_qblk) || !t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
         auto load_q = [&](int g) {
           if (ia[g] >= 1) mbar_wait(&S.q_empty[g], (ia[g] - 1) & 1);  // the group's last S of its previous item has read the tile
           mbar_expect_tx(&S.q_full[g], TILE_BYTES);
@@ -262,8 +275,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
     } else if (lane == 1) {
       // ------------------------------- V producer -------------------------------
       int T = 0;
-      for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
-        if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
+      for (t4_pos_init(pos, heads, Bn, n_qblk); pos.step < pos.n_steps; t4_pos_next(pos)) {
+        if (!t4_pos_decode(pos, heads, n_qblk) || !t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
         for (int t = 0; t < I.n_t; ++t, ++T) {
           const int s = T & 1;
           if (T >= 2) {
@@ -286,8 +299,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
       const uint32_t qa = smem_u32(S.q[g]);
       const uint32_t ts = tmem + (uint32_t)g * 128, to = tmem + O_COL + (uint32_t)g * HD;
       int it = 0, T0 = 0, J = 0, ia = 0;  // items seen, tiles before this item, halves of this group so far, items this group worked on
-      for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
-        if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
+      for (t4_pos_init(pos, heads, Bn, n_qblk); pos.step < pos.n_steps; t4_pos_next(pos)) {
+        if (!t4_pos_decode(pos, heads, n_qblk) || !t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
         const int n_g = g == 0 ? I.n_a : I.n_b;
         const int n_tg = g == 0 ? I.n_ta : I.n_tb;
         if (n_g > 0) mbar_wait(&S.q_full[g], ia & 1);
@@ -359,8 +372,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
     const uint32_t to = tmem + O_COL + (uint32_t)g * HD + lane_addr;
     int J = 0;
     [[maybe_unused]] int ord = 0;
-    for (t4_pos_init(pos, blockIdx.x, gridDim.x, heads, Bn); pos.w < n_items; t4_pos_next(pos, heads, Bn)) {
-      if (!t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
+    for (t4_pos_init(pos, heads, Bn, n_qblk); pos.step < pos.n_steps; t4_pos_next(pos)) {
+      if (!t4_pos_decode(pos, heads, n_qblk) || !t4_item<HD, CAUSAL, PACKED>(pos, n_qblk, heads, cap, cu_q, kv_past, I)) continue;
       const int n_g = g == 0 ? I.n_a : I.n_b;
       if (n_g == 0) continue;
       if (r == 0) T4_STAMP(g * 4 + 0, ord);  // item entered
