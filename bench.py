@@ -48,6 +48,67 @@ def parse():
     return ap.parse_args()
 
 
+def kernel_rooflines(dev):
+    """untimed extras: live rooflines of the two other kernels the north star names — K2 (prefill attention, tensor pipe) on the
+    L=2048 stress shape and on this workload's own shapes, K1 (select + gather/compact, HBM) on the 13B B=32 shape and on this
+    workload's 19 MB.  CUDA events over 20 back-to-back launches after 3 warm-ups; K1 rotates buffers beyond the 126 MB L2."""
+    import ctypes
+    import math
+    from dynamic_llava_b200._lib import lib
+    L = lib()
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = float(pk.get("bf16_tflops_sustained", 1400.0))
+    hbm_peak = float(pk.get("hbm_gbs", 6650.0))
+
+    def timeit(fn, n_rot=1, iters=20, warm=3):
+        for i in range(warm):
+            fn(i % n_rot)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i % n_rot)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = []
+    for name, B, nh, Lq in (("K2 dl_attn_prefill_tc4 L=2048 B=8 32 heads (stress)", 8, 32, 2048), ("K2 dl_attn_prefill_tc4 L=607 B=8 (layers 0-1)", 8, 32, 607),
+                            ("K2 dl_attn_prefill_tc4 L=146 B=8 (layers 2-31)", 8, 32, 146)):
+        hd, H, cap, N = 128, nh * 128, Lq + 8, B * Lq
+        qkv = torch.randn(N, 3 * H, device=dev, dtype=torch.bfloat16)
+        K = torch.randn(B, nh, cap, hd, device=dev, dtype=torch.bfloat16)
+        V = torch.randn(B, nh, cap, hd, device=dev, dtype=torch.bfloat16)
+        o = torch.empty(N, H, device=dev, dtype=torch.bfloat16)
+        cu = torch.arange(0, (B + 1) * Lq, Lq, device=dev, dtype=torch.int32)
+        past = torch.zeros(B, device=dev, dtype=torch.int32)
+        ms = timeit(lambda i: L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), 0, st()))
+        flop = 2.0 * Lq * Lq * H * B
+        out.append({"kernel": name, "bound": "tensor", "achieved": flop / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": flop / ms / 1e9 / tf_peak, "us": ms * 1e3, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"})
+        del qkv, K, V, o
+    for name, B, T, H in (("K1 dl_select_compact 13B B=32 P=2048 keep 0.2", 32, 1473, 5120), ("K1 dl_select_compact 7B B=8 P=607 keep 0.2 (this workload)", 8, 32, 4096)):
+        n_img, s0, k = 576, 5, 115
+        Pn = T - 1 + n_img
+        Pp = Pn - n_img + k
+        n_rot = max(2, int(300e6 // (B * Pn * H * 2)) + 1)
+        hid = [torch.randn(B, Pn, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
+        outb = [torch.empty(B, Pp, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
+        logits = torch.randn(B, n_img, 2, device=dev, dtype=torch.bfloat16)
+        keep = torch.empty(B, k, dtype=torch.int64, device=dev)
+        pos = torch.empty(B, Pp, dtype=torch.int32, device=dev)
+        cu = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        ms = timeit(lambda i: L.select_compact(P(logits), None, P(hid[i]), P(outb[i]), P(keep), P(pos), P(cu), B, Pn, H, s0, n_img, k, 0, st()), n_rot)
+        nbytes = 2 * B * Pp * H * 2 + B * n_img * 4 + B * Pp * 4
+        out.append({"kernel": name, "bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / ms / 1e6 / hbm_peak,
+                    "us": ms * 1e3, "algorithmic_bytes": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs"})
+        del hid, outb
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
@@ -246,7 +307,9 @@ def phase_and_roofline(model, eng, a, ids_d, pix_d, fd, dev):
     gemm_ms = s.elapsed_time(e) / reps
     peak, how = measured_peaks()
     achieved = bytes_total / (gemm_ms / 1e3) / 1e9
+    other = kernel_rooflines(dev)
     return {
+        "roofline_kernels": other,
         "phases": {"clip_prefill_ms": prefill_ms, "prefill_tokens_per_s": B * 607 / (prefill_ms / 1e3),
                    "decode_ms_per_token_step": None, "weight_gemm_ms_per_decode_step": gemm_ms},
         "roofline": {"bound": "hbm", "kernel": "skinny_gemm_kernel (decode weight streaming, TMA+tcgen05)", "achieved": achieved, "peak": peak,

@@ -53,6 +53,7 @@ struct T4Smem {
   alignas(8) uint64_t p_full[2][2];
   alignas(8) uint64_t o_done[2][2];
   alignas(8) uint64_t o_free[2];      // count 128: the group's softmax threads have read O out of TMEM
+  alignas(8) uint64_t stagger;        // count 128, ONE phase only: group A has stored its first P of the kernel
   uint32_t tmem_base;
   int32_t cu_s[64];                   // CSR header and past lengths of up to 63 samples: every role re-derives every item, and
   int32_t past_s[64];                 // two dependent global loads per item per role were ~1 k cycles at each item boundary
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
       mbar_init(&S.k_full[s], 1);
       mbar_init(&S.v_full[s], 1);
       mbar_init(&S.o_free[s], 128);
+      if (s == 0) mbar_init(&S.stagger, 128);
       for (int u = 0; u < 2; ++u) {
         mbar_init(&S.k_empty[s][u], 1);
         mbar_init(&S.v_empty[s][u], 1);
@@ -335,8 +337,11 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
           if ((j & 1) || j == n_g - 1) umma_commit(&S.v_empty[g][s]);
         };
         if (n_g > 0) {
-          // anti-phase start (first item only): group B begins one softmax pass after group A
-          if (it == 0 && g == 1) mbar_wait(&S.p_full[0][0], 0);
+          // Anti-phase start (first item only): group B begins one softmax pass after group A.  This must be a one-shot barrier:
+          // waiting on p_full[0][0] by parity deadlocks if this thread arrives after group A's THIRD half (phase 1 complete
+          // looks like phase 0 pending, and group A cannot reach phase 2 without the K/V stages group B has yet to release) —
+          // seen once in ~20 full-model prefills.
+          if (it == 0 && g == 1) mbar_wait(&S.stagger, 0);
           issue_s(0);
           if (n_g > 1) issue_s(1);
           if (ia >= 1) {  // O of the previous item must have been read out before PV(0) overwrites it
@@ -452,6 +457,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&S.p_full[g][jj & 1]);
+        if (g == 0 && jj == 0) mbar_arrive(&S.stagger);  // group A's first P of the kernel
       }
       if (r == 0) T4_STAMP(g * 4 + 2, ord);  // last P of the item stored
       // epilogue (the previous phase of this barrier, PV(jl - 2), is known complete: S(jl) was issued behind it)

@@ -536,6 +536,26 @@ def test_attn_prefill_tc4_persistent(L, q_lens, pasts, flags):
     _varlen_case(L, _call_tc4(L, flags), 128, True, q_lens, pasts, nh=2)
 
 
+@pytest.mark.timeout(180)
+def test_attn_prefill_tc4_repeated_launches_do_not_deadlock(L):
+    """regression: the anti-phase start of group B once waited on a parity of a multi-phase barrier and deadlocked when the issuer
+    arrived late (about one launch in twenty at full size).  400 launches on the workload's own prefill shape must all finish."""
+    B, nh, hd, Lq = 8, 32, 128, 607
+    H, cap, N = nh * hd, Lq + 1, B * Lq
+    qkv = torch.randn(N, 3 * H, device=DEV, dtype=BF)
+    K = torch.randn(B, nh, cap, hd, device=DEV, dtype=BF)
+    V = torch.randn(B, nh, cap, hd, device=DEV, dtype=BF)
+    o = torch.empty(N, H, device=DEV, dtype=BF)
+    cu = torch.arange(0, (B + 1) * Lq, Lq, device=DEV, dtype=torch.int32)
+    past = torch.zeros(B, device=DEV, dtype=torch.int32)
+    for i in range(400):
+        L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), i & 1, ST())
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all()
+
+
 @pytest.mark.parametrize("flags", [0, 1])
 def test_attn_prefill_tc4_persistent_many_items(L, flags):
     """more work items than SMs, ragged lengths and pasts: every CTA of the persistent kernel walks several items, some skipped,
