@@ -3,7 +3,7 @@
 // Serves every attention on the path whose head_dim is 64 (CLIP ViT-L/14, 577 tokens, non-causal — HF CLIPAttention;
 // VisionPredictor blocks, 576 tokens, non-causal — custom_transformer_layer.py:153-180) and is the small-sequence
 // path for the Llama prefill (head_dim 128, causal — dynamic_modeling_llama.py:1114-1122).  The tcgen05/TMEM kernel in
-// attn_prefill_tc.cu takes the large causal head_dim-128 tiles.
+// attn_prefill_tc4.cu (tcgen05, persistent) takes the causal head_dim-128 and the packed head_dim-64 cases.
 //
 // Per-sample extents come from a CSR header (`cu_q`, built by dl_select_compact) plus the arena's per-sample lengths,
 // so no padding is ever materialised: grid = (q tiles, heads, samples), out-of-range tiles exit.

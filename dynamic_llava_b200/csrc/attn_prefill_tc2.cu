@@ -1,5 +1,5 @@
 // K2 (v2): variable-length causal prefill attention, head_dim 128 — ping-pong tcgen05 pipeline.
-// Same contract as dl_attn_prefill_tc (attn_prefill_tc.cu); reference op: F.scaled_dot_product_attention(is_causal=True),
+// (The non-persistent form; the default is the persistent v4, attn_prefill_tc4.cu.)  Reference op: F.scaled_dot_product_attention(is_causal=True),
 // llava/model/language_model/dynamic_modeling_llama.py:1114-1122.
 //
 // One CTA = (256 query rows = two 128-row tiles A and B, one head, one sample); 320 threads:

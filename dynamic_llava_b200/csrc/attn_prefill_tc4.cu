@@ -1,19 +1,33 @@
 // K2 (v4): variable-length prefill attention — PERSISTENT tcgen05 pipeline.
-// Same contract as dl_attn_prefill_tc3 / dl_attn_packed_tc3 (attn_prefill_tc3.cu); reference op:
+// Same contract as dl_attn_prefill_tc2 / dl_attn_packed_tc (attn_prefill_tc2.cu); reference op:
 // F.scaled_dot_product_attention, llava/model/language_model/dynamic_modeling_llama.py:1114-1122 (causal, head_dim 128)
 // and custom_transformer_layer.py:153-180 / HF CLIPAttention (non-causal, head_dim 64).
 //
-// v3 (profiles/r1_ncu_attn_prefill_tc3.md) spends 11-15 k of ~36 k cycles per CTA outside the steady state: barrier init, TMEM
-// allocation, the first Q/K round trip, the O epilogue, teardown and the next CTA's launch — and with all 512 TMEM columns owned by
-// one CTA nothing else can run on the SM meanwhile.  v4 keeps v3's inner pipeline (64-key half tiles, two S buffers per group, one
-// MMA issuer per group, P and O resident in TMEM) and makes the CTA persistent: grid = #SMs, every CTA walks the work items
-// (256-row query block, head, sample) w = blockIdx.x, blockIdx.x + gridDim.x, ... of a list sorted heaviest-first (causal LPT).
-// All mbarriers live for the whole kernel and are indexed by running counters, so the roles drift across item boundaries:
-//   * the producers load the next item's Q (once both issuers have released it: q_empty) and K/V tiles while the softmax warps
-//     are still in the current item's last halves and epilogue;
+// Work item = (256 query rows = two 128-row groups A and B, one head, one sample).  CTA = 352 threads, one per SM:
+//   warp 0      lane 0: Q + K producer, lane 1: V producer (TMA, 128-key tiles in 2-stage rings, HD/64 SW128 boxes per tile);
+//   warp 1, 10  MMA issuers, one elected thread per group.  Per 64-key half j:  PV(j) S(j+2);
+//   warps 2-5   softmax group A, warps 6-9 group B: one thread per query row (TMEM lane == row).
+// TMEM (all 512 columns): S_A0 [0,64) S_A1 [64,128) S_B0 [128,192) S_B1 [192,256) O_A [256,256+HD) O_B [256+HD,256+2HD).
+//   * 64-key HALF tiles with two S buffers per group: S(j+1) is complete in TMEM when softmax(j) ends and S(j+2) is issued right
+//     behind PV(j), so neither the softmax warps nor the tensor pipe wait for the other's latency (v2's serial chain);
+//   * S is read ONCE into registers, P = exp2(S*scale - m) is written back as packed bf16 over the first 32 columns of the same
+//     buffer and consumed from TMEM as the A operand of the PV MMA; O accumulates in TMEM, V is an MN-major B operand in place;
+//   * the running max is only refreshed (and O rescaled) when it grows by more than 2^8 (exact after the final 1/l);
+//   * EXP_POLY: one exp2 in four on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. error 7.5e-5);
+//   * O leaves through shared memory: 32-row x 64-column boxes (128B swizzle) written with TMA stores.  A row-per-thread store
+//     straight from registers is 32 scattered 16-byte requests per instruction and cost ~16 k cycles per item.
+// Persistence: grid = #SMs; all mbarriers live for the whole kernel and are indexed by running counters, so the roles drift across
+// item boundaries:
+//   * the producers load the next item's Q (per group, once that group's issuer has released it) and K/V tiles while the softmax
+//     warps are still in the current item's last halves and epilogue;
 //   * the issuers compute S(0), S(1) of the next item under the current epilogue; only PV(0) waits for o_free (O read out);
 //   * every group releases every K/V stage of every item exactly once (tcgen05.commit, also for tiles it did not read), which
-//     keeps the per-group empty barriers in step with the producers' running tile counter.
+//     keeps the per-group empty barriers in step with the producers' running tile counter;
+//   * every parity wait targets a phase that can be at most ONE ahead of the waiter (the anti-phase start of group B uses its own
+//     one-shot barrier for that reason).
+// Schedule (t4_pos_*): (sample, head) pairs in L2-sized windows, items sorted heaviest-first inside a window and dealt out as a snake.
+// History and measurements: profiles/r1_ncu_attn_prefill_tc3.md (non-persistent v3, source in the git history),
+// profiles/r1_ncu_attn_prefill_tc4.md.
 #include <cuda.h>
 
 #include "common.cuh"

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DL_B200_ABI_VERSION 1
+#define DL_B200_ABI_VERSION 2  /* 2: persistent attention (tc4) entry points added, v1 tcgen05 attention removed */
 
 int dl_version(void);
 const char* dl_last_error_string(void);
