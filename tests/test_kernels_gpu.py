@@ -536,6 +536,13 @@ def test_attn_prefill_tc4_persistent(L, q_lens, pasts, flags):
     _varlen_case(L, _call_tc4(L, flags), 128, True, q_lens, pasts, nh=2)
 
 
+def test_attn_prefill_tc4_more_than_63_samples(L):
+    """B >= 64: the CSR header no longer fits the kernel's shared-memory copy and is read from global memory per item"""
+    q_lens = [1 + (7 * i) % 40 for i in range(70)]
+    pasts = [(3 * i) % 11 for i in range(70)]
+    _varlen_case(L, _call_tc4(L, 0), 128, True, q_lens, pasts, nh=2)
+
+
 @pytest.mark.timeout(180)
 def test_attn_prefill_tc4_repeated_launches_do_not_deadlock(L):
     """regression: the anti-phase start of group B once waited on a parity of a multi-phase barrier and deadlocked when the issuer
