@@ -536,6 +536,30 @@ def test_attn_prefill_tc4_persistent(L, q_lens, pasts, flags):
     _varlen_case(L, _call_tc4(L, flags), 128, True, q_lens, pasts, nh=2)
 
 
+@pytest.mark.parametrize("B,nh,Lq,Lk", [(2, 4, 300, 300), (1, 2, 64, 200), (3, 2, 129, 129)])
+def test_integration_stub_sdpa_prefill(L, B, nh, Lq, Lk):
+    """the kernel-level binding shown in INTEGRATION.md: the reference's own tensors (query_states as a transpose(1, 2) view of the
+    token-major projection, contiguous [B, heads, Lk, 128] keys/values) go in unchanged and the result equals causal SDPA with the
+    query block aligned to the END of the keys (dynamic_modeling_llama.py:1114-1122)"""
+    hd = 128
+    g = torch.Generator().manual_seed(7)
+    proj = (torch.randn(B, Lq, nh * hd, generator=g)).to(BF).to(DEV)          # what q_proj returns
+    q = proj.view(B, Lq, nh, hd).transpose(1, 2)                              # query_states
+    k = torch.randn(B, nh, Lk, hd, generator=g).to(BF).to(DEV)
+    v = torch.randn(B, nh, Lk, hd, generator=g).to(BF).to(DEV)
+    q2 = q.transpose(1, 2).reshape(B * Lq, nh * hd)
+    assert q2.data_ptr() == proj.data_ptr()                                   # no copy
+    out = torch.empty_like(q2)
+    cu = torch.arange(0, (B + 1) * Lq, Lq, dtype=torch.int32, device=DEV)
+    past = torch.full((B,), Lk - Lq, dtype=torch.int32, device=DEV)
+    L.attn_prefill_tc4(P(q2), nh * hd, P(k), P(v), P(out), nh * hd, P(cu), P(past), B * Lq, B, nh, Lk, Lq, hd ** -0.5, 0, ST())
+    torch.cuda.synchronize()
+    got = out.view(B, Lq, nh, hd).transpose(1, 2).float()
+    mask = torch.ones(Lq, Lk, dtype=torch.bool, device=DEV).tril(diagonal=Lk - Lq)
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=mask)
+    assert (got - ref).abs().max().item() < 2e-2
+
+
 def test_attn_prefill_tc4_more_than_63_samples(L):
     """B >= 64: the CSR header no longer fits the kernel's shared-memory copy and is read from global memory per item"""
     q_lens = [1 + (7 * i) % 40 for i in range(70)]
