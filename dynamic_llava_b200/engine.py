@@ -57,6 +57,8 @@ class Session:
         D = c.sparse_config["d_model"]
         self.tp_ln = e(B, H)
         self.tp_logits = e(B, 2)
+        self.tp_partial = e(8 * B * D, dtype=torch.float32)  # split-K slices of the text predictor's first Linear (own buffer: it
+        # runs on a side stream next to the QKV GEMM, which owns `partial`)
         self.forced_buf = torch.zeros(max(max_new, 1), B, device=dev, dtype=torch.uint8)
         self.forced = None  # uint8 [n_steps, B] (forced_buf when a forced decision stream is in use)
         self.attn_ws = None
@@ -89,6 +91,7 @@ class Engine:
         self.packed = None
         # "tc4" (default: persistent tcgen05 kernel) | "tc2" (non-persistent tcgen05) | "mma" (warp-MMA tile path)
         self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc4")
+        self.side_stream = torch.cuda.Stream(device=self.device)  # text-predictor branch of the decode step
         self.attn_flags = int(os.environ.get("DLB200_ATTN_FLAGS", "0"))  # dl_attn_prefill_tc4 flags (bit 0: FMA-pipe exp2)
         self.packed_attn = os.environ.get("DLB200_PACKED_ATTN", "tc")  # CLIP / predictor attention: "tc" (tcgen05) | "mma"
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
@@ -495,8 +498,10 @@ class Engine:
         return s
 
     def _n_split(self, B, heads, ub_len):
+        # split only when the (sample, head) CTAs alone cannot fill the SMs AND every split still gets >= 512 keys: at config 2's
+        # layers 0-1 (B*heads = 256, 735 keys) one pass is faster than two splits + combine (22.3 vs 26.0 us, r1_microbench_v1.json)
         want = (2 * 148 + B * heads - 1) // (B * heads)
-        return max(1, min(want, ub_len // 256, 16))
+        return max(1, min(want, ub_len // 512, 16))
 
     def decode_layers(self, sess: Session, use_decisions: bool, quirk: bool):
         """embed(next_ids) -> L decoder layers -> final norm -> lm_head: writes sess.logits (bf16 [B,V])."""
@@ -515,24 +520,37 @@ class Engine:
         L_.rmsnorm(_p(sess.xres), _p(pk["layers"][0]["ln1"]), _p(sess.xn), B, H, eps, st)
         self.launches += 2
         keep = None
+        join_side = False
         for l in range(Lyr):
             W = pk["layers"][l]
             if l == SL and use_decisions:
                 tp = m.output_text_score_predictor.output_mlp
                 D = tp[1].weight.shape[0]
-                L_.layernorm(_p(sess.xres), _p(tp[0].weight), _p(tp[0].bias), _p(sess.tp_ln), B, H, tp[0].eps, st)
-                s = self._gemm(sess, sess.tp_ln, tp[1].weight, B, D, H)
-                L_.text_decision(_p(sess.partial), s, B, D, _p(tp[1].bias), _p(tp[3].weight), _p(tp[3].bias), _p(tp[5].weight),
+                # The predictor (LayerNorm -> Linear(H->D) -> MLP tail -> decision) only needs this layer's INPUT and its result is
+                # first consumed by this layer's attention kernel: it runs on a side stream next to the layer's QKV GEMM (fork /
+                # join are graph-capturable) instead of ~30 us in series on every decode step.
+                cur = torch.cuda.current_stream()
+                side = self.side_stream
+                side.wait_stream(cur)
+                sst = ctypes.c_void_p(side.cuda_stream)
+                s_tp = L_.skinny_gemm_splits(D, H, self.skinny_target_ctas)
+                L_.layernorm(_p(sess.xres), _p(tp[0].weight), _p(tp[0].bias), _p(sess.tp_ln), B, H, tp[0].eps, sst)
+                L_.skinny_gemm(_p(sess.tp_ln), _p(tp[1].weight), _p(sess.tp_partial), B, D, H, s_tp, self.l2_prefetch_mb, sst)
+                L_.text_decision(_p(sess.tp_partial), s_tp, B, D, _p(tp[1].bias), _p(tp[3].weight), _p(tp[3].bias), _p(tp[5].weight),
                                  _p(tp[5].bias), _p(tp[7].weight), _p(tp[7].bias), _p(sess.forced), _p(a.step), -1, _p(a.keep),
-                                 _p(sess.tp_logits), st)
-                self.launches += 2
+                                 _p(sess.tp_logits), sst)
+                self.launches += 3
                 keep = a.keep
+                join_side = True
             K_, V_, cap = a.layer(l)
             kvl = a.kv_len[l]
             s = self._gemm(sess, sess.xn, W["wqkv"], B, 3 * H, H)
             ns = self._n_split(B, nh, cap)
             if ns > 1 and sess.attn_ws is None:
                 sess.attn_ws = torch.empty(L_.attn_decode_workspace_bytes(B, nh, 16) // 4, device=self.device, dtype=torch.float32)
+            if join_side:  # the keep decision must be there before this layer's attention appends (or not) the new token's K/V
+                torch.cuda.current_stream().wait_stream(self.side_stream)
+                join_side = False
             L_.attn_decode_fused(_p(sess.partial), s, _p(a.pos), _p(keep if l >= SL else None), _p(pk["cos"]), _p(pk["sin"]), _p(K_), _p(V_),
                                  _p(kvl), _p(sess.attn), _p(sess.attn_ws), B, nh, hd, cap, ns, scale,
                                  1 if (quirk and l >= SL and keep is not None) else 0,
