@@ -91,6 +91,21 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   const int n_keys = max(k1 - k0, 0);
   const int n_tiles = (n_keys + AD_TK - 1) / AD_TK;
   const bool fused = fz.partial != nullptr;
+  const bf16* kbase = k_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
+  const bf16* vbase = v_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
+  // The cached length is known now: every remaining K/V tile that still has a free ring stage goes out BEFORE the QKV reduce +
+  // RoPE front end below (two dependent L2 round trips and a block barrier), not after it.  Rows below `len` were written by
+  // earlier steps; this step's own row (slot `len`) is served from shared memory.
+  int n_issued = n_pre;
+  if (threadIdx.x == AD_CWARPS * 32) {
+    for (; n_issued < n_tiles && n_issued < AD_STAGES; ++n_issued) {
+      const int keys = min(AD_TK, n_keys - n_issued * AD_TK);
+      const uint32_t bytes = keys * AD_HD * 2;
+      mbar_expect_tx(&S.full[n_issued], 2 * bytes);
+      tma_bulk_g2s(S.kv[n_issued][0], kbase + (int64_t)n_issued * AD_TK * AD_HD, bytes, &S.full[n_issued]);
+      tma_bulk_g2s(S.kv[n_issued][1], vbase + (int64_t)n_issued * AD_TK * AD_HD, bytes, &S.full[n_issued]);
+    }
+  }
   if (fz.l2_prefetch != nullptr && threadIdx.x == 32) {
     const int64_t n_cta = (int64_t)gridDim.x * gridDim.y * gridDim.z;
     const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -157,13 +172,10 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   }
   __syncthreads();
 
-  const bf16* kbase = k_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
-  const bf16* vbase = v_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
-
   if (warp == AD_CWARPS) {
     // ---------------- producer warp: TMA bulk copies ----------------
     if (lane == 0) {
-      for (int t = n_pre; t < n_tiles; ++t) {
+      for (int t = n_issued; t < n_tiles; ++t) {
         const int s = t % AD_STAGES;
         const uint32_t ph = (t / AD_STAGES) & 1;
         mbar_wait(&S.empty[s], ph ^ 1);
