@@ -7,16 +7,18 @@
 // select on the 16-bit score keys (256-bin histogram of the high byte, then of the low byte inside the boundary bin,
 // warp-aggregated with match.any so equal keys cost one shared atomic per warp), followed by an ordered compaction
 // scan; replicating it per CTA is cheaper than a second kernel or a round trip of the index map through HBM.
-// The rows move through a shared-memory ring of whole-row slots driven by ONE thread with bulk async copies
+// The rows move through a shared-memory ring of whole-row slots driven by ONE thread (warp 0) with bulk async copies
 // (cp.async.bulk global->shared on an mbarrier, shared->global in bulk groups): no register staging, 64 KB in flight per
-// CTA.  Rows are visited text-first: the [left | right] text rows do not depend on the selection, so their loads are
-// issued BEFORE the selection runs and the radix select hides under the first HBM round trip.
+// CTA.  Rows are visited text-first: the [left | right] text rows do not depend on the selection, so the copy thread streams
+// them from the first cycle while warps 1-8 run the radix select on their own named barrier; it only waits (mbarrier
+// `sel_done`) right before its first IMAGE row.
 // Ties at the k-th score are broken towards the lower index (= stable descending sort).
 // HBM-bound: algorithmic bytes = 2 * B * P' * H * 2.
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
 
-#define SC_THREADS 256
+#define SC_THREADS 256           // selection threads (warps 1-8)
+#define SC_BLOCK (SC_THREADS + 32)  // + warp 0: the copy engine driver
 #define SC_MAX_IMG 1024
 #define SC_MAX_SLOTS 16
 #define SC_RING_BYTES 65536
@@ -41,7 +43,9 @@ DL_DEVINL void hist_add_aggregated(int* hist, int bin, bool valid) {
   }
 }
 
-__global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
+DL_DEVINL void sel_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the selection threads only
+
+__global__ void __launch_bounds__(SC_BLOCK) select_compact_kernel(
     const bf16* __restrict__ logits,         // [B, n_img, 2]
     const int64_t* __restrict__ forced_keep, // [B, k] or null
     const bf16* __restrict__ hid_in,         // [B, P, H]
@@ -52,12 +56,14 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
     int P, int H, int s0, int n_img, int k, int n_slots) {
   extern __shared__ __align__(128) uint8_t ring[];  // n_slots whole rows
   __shared__ __align__(8) uint64_t full[SC_MAX_SLOTS];
+  __shared__ __align__(8) uint64_t sel_done;  // count SC_THREADS: kidx[] is final
   __shared__ uint16_t key[SC_MAX_IMG];
   __shared__ int16_t kidx[SC_MAX_IMG];
   __shared__ int hist[256];
   __shared__ int wsum[SC_THREADS / 32];
   __shared__ int sel[4];  // [0] boundary bin, [1] #keys above it
-  const int b = blockIdx.y, tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int tid = (int)threadIdx.x - 32;  // selection thread index; warp 0 (tid < 0) drives the copies
   const int R = gridDim.x, r = blockIdx.x;
   const int Pp = P - n_img + k;
   const int n_text = Pp - k;
@@ -69,19 +75,47 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
   const int n_mine = r < Pp ? (Pp - r + R - 1) / R : 0;
   int issued = 0;
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     for (int s = 0; s < n_slots; ++s) mbar_init(&full[s], 1);
+    mbar_init(&sel_done, SC_THREADS);
     fence_barrier_init();
-    // text rows need no selection: start their loads now
-    while (issued < n_mine && issued < n_slots) {
-      const int v = r + issued * R;
-      if (v >= n_text) break;
-      const int sj = v < s0 ? v : v + n_img;
-      mbar_expect_tx(&full[issued], row_bytes);
-      tma_bulk_g2s(ring + (size_t)issued * row_bytes, in_b + (int64_t)sj * H, row_bytes, &full[issued]);
-      ++issued;
-    }
   }
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    // ---- copy engine: ring of whole-row slots, loads n_slots - 1 deep, stores in bulk groups.  It never takes part in the
+    // selection: text rows flow from the first cycle, and it only waits for kidx[] right before its first IMAGE row. ----
+    bool sel_ready = false;
+    auto src_row = [&](int v) {
+      if (v < n_text) return v < s0 ? v : v + n_img;
+      if (!sel_ready) {
+        mbar_wait(&sel_done, 0);
+        sel_ready = true;
+      }
+      return s0 + (int)kidx[v - n_text];
+    };
+    auto dst_row = [&](int v) { return v < n_text ? (v < s0 ? v : v + k) : s0 + (v - n_text); };
+    auto issue_load = [&](int i) {
+      const int s = i % n_slots;
+      const int sj = src_row(r + i * R);
+      mbar_expect_tx(&full[s], row_bytes);
+      tma_bulk_g2s(ring + (size_t)s * row_bytes, in_b + (int64_t)sj * H, row_bytes, &full[s]);
+    };
+    while (issued < n_mine && issued < n_slots) issue_load(issued++);
+    for (int i = 0; i < n_mine; ++i) {
+      const int s = i % n_slots;
+      mbar_wait(&full[s], (uint32_t)(i / n_slots) & 1u);
+      bulk_s2g(out_b + (int64_t)dst_row(r + i * R) * H, ring + (size_t)s * row_bytes, row_bytes);
+      bulk_commit();
+      if (i >= 1 && issued < n_mine) {  // slot of row i-1 is free once its store has read it
+        bulk_wait_read<1>();
+        issue_load(issued++);
+      }
+    }
+    bulk_wait_read<0>();
+    return;
+  }
+  if (tid < 0) return;  // the rest of warp 0
 
   if (forced_keep != nullptr) {
     for (int i = tid; i < k; i += SC_THREADS) kidx[i] = (int16_t)forced_keep[(int64_t)b * k + i];
@@ -101,7 +135,7 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
     const int n_round = (n_img + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
     for (int pass = 0; pass < 2; ++pass) {
       if (tid < 256) hist[tid] = 0;
-      __syncthreads();
+      sel_sync();
       for (int i = tid; i < n_round; i += SC_THREADS) {  // whole warps stay converged for match.any
         const int kk = i < n_img ? key[i] : 0;
         if (pass == 0)
@@ -109,7 +143,7 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
         else
           hist_add_aggregated(hist, kk & 255, i < n_img && (kk >> 8) == prefix);
       }
-      __syncthreads();
+      sel_sync();
       if (tid < 32) {  // suffix scan over the 256 bins (8 per lane), locate the bin that holds the `want`-th largest
         int loc = 0;
 #pragma unroll
@@ -130,12 +164,12 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
           run += h;
         }
       }
-      __syncthreads();
+      sel_sync();
       if (pass == 0) prefix = sel[0];
       c_gt += sel[1];
       want -= sel[1];
       if (pass == 1) prefix = (prefix << 8) | sel[0];
-      __syncthreads();
+      sel_sync();
     }
     const int T = prefix, need_eq = k - c_gt;
     // ordered compaction: contiguous chunk per thread, block exclusive scan of (#gt, #eq) packed in one int
@@ -150,7 +184,7 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
       if ((tid & 31) >= o) inc += t;
     }
     if ((tid & 31) == 31) wsum[tid >> 5] = inc;
-    __syncthreads();
+    sel_sync();
     int base = 0;
     for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
     const int excl = base + inc - cnt;
@@ -166,36 +200,16 @@ __global__ void __launch_bounds__(SC_THREADS) select_compact_kernel(
       }
     }
   }
-  __syncthreads();
+  sel_sync();
 
-  if (tid == 0) {
-    // ---- copy engine: ring of whole-row slots, loads n_slots - 1 deep, stores in bulk groups ----
-    auto src_row = [&](int v) { return v < n_text ? (v < s0 ? v : v + n_img) : s0 + (int)kidx[v - n_text]; };
-    auto dst_row = [&](int v) { return v < n_text ? (v < s0 ? v : v + k) : s0 + (v - n_text); };
-    auto issue_load = [&](int i) {
-      const int s = i % n_slots;
-      mbar_expect_tx(&full[s], row_bytes);
-      tma_bulk_g2s(ring + (size_t)s * row_bytes, in_b + (int64_t)src_row(r + i * R) * H, row_bytes, &full[s]);
-    };
-    while (issued < n_mine && issued < n_slots) issue_load(issued++);
-    for (int i = 0; i < n_mine; ++i) {
-      const int s = i % n_slots;
-      mbar_wait(&full[s], (uint32_t)(i / n_slots) & 1u);
-      bulk_s2g(out_b + (int64_t)dst_row(r + i * R) * H, ring + (size_t)s * row_bytes, row_bytes);
-      bulk_commit();
-      if (i >= 1 && issued < n_mine) {  // slot of row i-1 is free once its store has read it
-        bulk_wait_read<1>();
-        issue_load(issued++);
-      }
-    }
-    bulk_wait_read<0>();
-  } else if (r == 0) {  // index map + CSR header
-    for (int i = tid - 1; i < k; i += SC_THREADS - 1) keep_index[(int64_t)b * k + i] = kidx[i];
-    for (int j = tid - 1; j < Pp; j += SC_THREADS - 1) {
+  mbar_arrive(&sel_done);  // release: kidx[] is visible to the copy thread's acquire
+  if (r == 0) {  // index map + CSR header
+    for (int i = tid; i < k; i += SC_THREADS) keep_index[(int64_t)b * k + i] = kidx[i];
+    for (int j = tid; j < Pp; j += SC_THREADS) {
       int p = j < s0 ? j : (j < s0 + k ? s0 + kidx[j - s0] : j + (n_img - k));
       pos_out[(int64_t)b * Pp + j] = p;
     }
-    if (tid == 1) {
+    if (tid == 0) {
       cu_seqlens[b + 1] = (b + 1) * Pp;
       if (b == 0) cu_seqlens[0] = 0;
     }
@@ -222,10 +236,16 @@ extern "C" int dl_select_compact(const void* logits, const int64_t* forced_keep,
     attr_set = true;
   }
   int R = ctas_per_sample;
-  if (R <= 0) R = (148 * 3 + B - 1) / B;  // three 64 KB rings resident per SM
+  if (R <= 0) {
+    // measured (tools/k1_sweep.py): text rows stream best in short CTAs (~10 rows each; more, shorter CTAs also even out the
+    // tail), image rows in long ones (every CTA repeats the ~3 us select before its first image row)
+    const int n_text = Pp - k;
+    R = (n_text + 9) / 10 + (k + 71) / 72;
+    if (R * B < 148) R = (148 + B - 1) / B;  // small problems: at least one CTA per SM
+  }
   if (R > Pp) R = Pp;
   if (R < 1) R = 1;
-  select_compact_kernel<<<dim3(R, B), SC_THREADS, smem, stream>>>((const bf16*)logits, forced_keep, (const bf16*)hidden_in,
+  select_compact_kernel<<<dim3(R, B), SC_BLOCK, smem, stream>>>((const bf16*)logits, forced_keep, (const bf16*)hidden_in,
                                                                   (bf16*)hidden_out, keep_index, pos_out, cu_seqlens, P, H,
                                                                   img_start, n_img, k, n_slots);
   DL_CHECK_LAUNCH("dl_select_compact");
