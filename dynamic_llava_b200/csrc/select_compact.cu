@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(SC_BLOCK) select_compact_kernel(
 
   if (forced_keep != nullptr) {
     for (int i = tid; i < k; i += SC_THREADS) kidx[i] = (int16_t)forced_keep[(int64_t)b * k + i];
+  } else if (k == n_img) {  // keep rate 1.0: the ascending indices of ALL tokens, whatever the scores
+    for (int i = tid; i < k; i += SC_THREADS) kidx[i] = (int16_t)i;
   } else if (k > 0) {
     // scores rounded where the reference's bf16 log_softmax rounds, mapped to order-preserving 16-bit keys
     for (int i = tid; i < n_img; i += SC_THREADS) {
@@ -239,8 +241,8 @@ extern "C" int dl_select_compact(const void* logits, const int64_t* forced_keep,
   if (R <= 0) {
     // measured (tools/k1_sweep.py): text rows stream best in short CTAs (~10 rows each; more, shorter CTAs also even out the
     // tail), image rows in long ones (every CTA repeats the ~3 us select before its first image row)
-    const int n_text = Pp - k;
-    R = (n_text + 9) / 10 + (k + 71) / 72;
+    const int n_free = (k == n_img && forced_keep == nullptr) ? Pp : Pp - k;  // rows whose source is known without the select
+    R = (n_free + 9) / 10 + (Pp - n_free + 71) / 72;
     if (R * B < 148) R = (148 + B - 1) / B;  // small problems: at least one CTA per SM
   }
   if (R > Pp) R = Pp;
