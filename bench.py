@@ -51,7 +51,8 @@ def parse():
 def kernel_rooflines(dev):
     """untimed extras: live rooflines of the two other kernels the north star names — K2 (prefill attention, tensor pipe) on the
     L=2048 stress shape and on this workload's own shapes, K1 (select + gather/compact, HBM) on the 13B B=32 shape and on this
-    workload's 19 MB.  CUDA events over 20 back-to-back launches after 3 warm-ups; K1 rotates buffers beyond the 126 MB L2."""
+    workload's 19 MB.  CUDA events over back-to-back launches (K2: 50 after 10 warm-ups, K1: 20 after 3); K1 rotates buffers beyond
+    the 126 MB L2."""
     import ctypes
     import math
     from dynamic_llava_b200._lib import lib
@@ -84,7 +85,8 @@ def kernel_rooflines(dev):
         o = torch.empty(N, H, device=dev, dtype=torch.bfloat16)
         cu = torch.arange(0, (B + 1) * Lq, Lq, device=dev, dtype=torch.int32)
         past = torch.zeros(B, device=dev, dtype=torch.int32)
-        ms = timeit(lambda i: L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), 0, st()))
+        ms = timeit(lambda i: L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), 0, st()),
+                    iters=50, warm=10)
         flop = 2.0 * Lq * Lq * H * B
         out.append({"kernel": name, "bound": "tensor", "achieved": flop / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": flop / ms / 1e9 / tf_peak, "us": ms * 1e3, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"})
