@@ -92,6 +92,7 @@ class Engine:
         # "tc4" (default: persistent tcgen05 kernel) | "tc2" (non-persistent tcgen05) | "mma" (warp-MMA tile path)
         self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc4")
         self.side_stream = torch.cuda.Stream(device=self.device)  # text-predictor branch of the decode step
+        self._cu_cache = {}
         self.attn_flags = int(os.environ.get("DLB200_ATTN_FLAGS", "0"))  # dl_attn_prefill_tc4 flags (bit 0: FMA-pipe exp2)
         self.packed_attn = os.environ.get("DLB200_PACKED_ATTN", "tc")  # CLIP / predictor attention: "tc" (tcgen05) | "mma"
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
@@ -201,7 +202,9 @@ class Engine:
         """non-causal attention over a fused [B*N, 3*heads*hd] projection (CLIP, predictor blocks)."""
         C = heads * hd
         out = torch.empty(B * N, C, device=qkv.device, dtype=qkv.dtype)
-        cu = torch.arange(0, (B + 1) * N, N, device=qkv.device, dtype=torch.int32)
+        cu = self._cu_cache.get((B, N))  # one CSR header per shape, not one arange launch per attention call (57 per prefill)
+        if cu is None:
+            cu = self._cu_cache[(B, N)] = torch.arange(0, (B + 1) * N, N, device=qkv.device, dtype=torch.int32)
         if hd == 64 and not causal and self.packed_attn == "tc":
             if self.prefill_attn == "tc4":
                 self.L.attn_packed_tc4(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), self.attn_flags, _stream())
