@@ -351,3 +351,79 @@ def test_multiround_continuation_over_ragged_cache():
     top2 = g["cont_logits"].topk(2, dim=-1).values
     sure = (top2[..., 0] - top2[..., 1]) > 0.08 * scale
     assert torch.equal(cont.argmax(-1)[sure], g["cont_logits"].argmax(-1)[sure])
+
+
+@pytest.mark.timeout(300)
+def test_full_size_7b_config2_properties():
+    """BASELINE config 2 at FULL size (LLaVA-1.5-7B dims, B=8, 32-id prompt + 336x336 image, keep 0.2, forced Bernoulli(0.5) output
+    decisions) — too big for the CPU oracle, so checked through size-independent properties of the reference's algorithm:
+      * KV bookkeeping: layers < sparse_layer hold P + n - 1 keys, layers >= sparse_layer hold P' + (#kept decisions) keys, per sample
+        (cache_utils.py:146-250), with P = 607 and P' = 146 (dynamic_modeling_llama.py:1899-1951);
+      * greedy decode is a pure function of the inputs: two generate() calls (CUDA-graph replay) and the eager loop agree token for
+        token; a half batch reproduces the per-sample KV bookkeeping (samples never interact)."""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    from dynamic_llava_b200.presets import preset
+    from dynamic_llava_b200.synthetic import device_state_dict, forced_text_decisions, synthetic_inputs
+    cfgd = preset("llava-1.5-7b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = True
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device="cuda")
+    model.get_vision_tower().load_model()
+    model.load_state_dict(device_state_dict(cfgd, seed=0, device="cuda"), strict=True)
+    B, T, n_new = 8, 32, 12
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    ids, pix = ids.cuda(), pix.cuda()
+    fd = forced_text_decisions(n_new - 1, B, keep_rate=0.5, seed=3)
+    kw = dict(images=pix, max_new_tokens=n_new, do_sample=False, eos_token_id=None, forced_text_decisions=fd)
+    out1 = model.generate(ids, **kw).cpu()
+    sess = next(iter(model._sessions.values()))
+    lens = sess.arena.kv_len.cpu().long()
+    SL, L = cfgd["sparse_config"]["sparse_layer"], cfgd["num_hidden_layers"]
+    P, k = T - 1 + 576, int(576 * 0.2)
+    Pp = P - 576 + k
+    assert (P, Pp) == (607, 146)
+    assert lens[:SL].eq(P + n_new - 1).all()
+    kept = fd.sum(0).long()  # decisions of the n_new - 1 decode steps
+    for l in range(SL, L):
+        assert lens[l].tolist() == (Pp + kept).tolist(), l
+    out2 = model.generate(ids, **kw).cpu()
+    assert torch.equal(out1, out2)
+    out3 = model.generate(ids, use_cuda_graph=False, **kw).cpu()
+    assert torch.equal(out1, out3)
+    # samples never interact: a half batch keeps the same per-sample bookkeeping (token equality across batch sizes is not a
+    # property: the library GEMMs of the prefill pick M-dependent kernels and random-init logits have no margin)
+    model.generate(ids[:4], images=pix[:4], max_new_tokens=n_new, do_sample=False, eos_token_id=None, forced_text_decisions=fd[:, :4])
+    lens_half = [s_ for s_ in model._sessions.values() if s_.B == 4][0].arena.kv_len.cpu().long()
+    assert torch.equal(lens_half, lens[:, :4])
+    assert out1.shape == (B, n_new) and int(out1.min()) >= 0 and int(out1.max()) < cfgd["vocab_size"]
+
+
+@pytest.mark.timeout(400)
+def test_full_size_13b_config4_prefill_properties():
+    """BASELINE config 4 per GPU (LLaVA-1.5-13B dims, B=4, full embedded length P = 2048 -> P' = 1587 at keep 0.2, prefill + 2 tokens),
+    through the same size-independent properties: KV bookkeeping per layer class, determinism, half-batch bookkeeping (the long-sequence
+    prefill attention and the 130 MB select + gather/compact run at their full sizes here)."""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    from dynamic_llava_b200.synthetic import device_state_dict
+    cfgd = preset("llava-1.5-13b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = False
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device="cuda")
+    model.get_vision_tower().load_model()
+    model.load_state_dict(device_state_dict(cfgd, seed=0, device="cuda"), strict=True)
+    B, T, n_new = 4, 2048 - 576 + 1, 2
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    ids, pix = ids.cuda(), pix.cuda()
+    kw = dict(max_new_tokens=n_new, do_sample=False, eos_token_id=None)
+    out1 = model.generate(ids, images=pix, **kw).cpu()
+    lens = next(iter(model._sessions.values())).arena.kv_len.cpu().long()
+    SL = cfgd["sparse_config"]["sparse_layer"]
+    P, k = T - 1 + 576, int(576 * 0.2)
+    assert P == 2048
+    assert lens[:SL].eq(P + n_new - 1).all() and lens[SL:].eq(P - 576 + k + n_new - 1).all()
+    assert torch.equal(out1, model.generate(ids, images=pix, **kw).cpu())
+    # samples never interact: a half batch has the same per-sample bookkeeping (token equality across batch sizes is not a property:
+    # the library GEMMs of the prefill pick M-dependent kernels and random-init logits have no margin)
+    model.generate(ids[:2], images=pix[:2], **kw)
+    lens_half = [s_ for s_ in model._sessions.values() if s_.B == 2][0].arena.kv_len.cpu().long()
+    assert torch.equal(lens_half, lens[:, :2])
+    del model
+    torch.cuda.empty_cache()
