@@ -48,6 +48,13 @@ __global__ void __launch_bounds__(RN_THREADS) dec_reduce_residual_norm_kernel(co
                                                                               const bf16* __restrict__ w, bf16* __restrict__ xn, int M,
                                                                               int H, int S, float eps) {
   __shared__ float red[32];
+  // the norm weight is a constant of the model: fetch it BEFORE the dependency wait, off the critical path
+  uint2 wraw[RN_V];
+#pragma unroll
+  for (int v = 0; v < RN_V; ++v) {
+    const int i = (threadIdx.x + v * RN_THREADS) * 4;
+    wraw[v] = (w != nullptr && i < H) ? *reinterpret_cast<const uint2*>(w + i) : make_uint2(0u, 0u);
+  }
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(RN_THREADS) dec_reduce_residual_norm_kernel(co
   for (int v = 0; v < RN_V; ++v) {
     const int i = (threadIdx.x + v * RN_THREADS) * 4;
     if (i < H) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(w + i);
+      const uint2 raw = wraw[v];
       const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
       const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
       __nv_bfloat162 lo = __floats2bfloat162_rn(w01.x * rbf(r[v][0] * rstd), w01.y * rbf(r[v][1] * rstd));
