@@ -83,14 +83,18 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   }
   pdl_launch_dependents();
   pdl_wait();  // q, side k/v, kv_len and the arena rows of this step come from predecessor kernels
+  // every scalar this CTA needs goes out in ONE round trip (len, position, keep flag), and the cos/sin row that depends on the
+  // position right behind it, so that the front end below costs two dependent L2 round trips instead of four
+  const bool fused = fz.partial != nullptr;
   const int len = kv_len[b];
+  const int pos_b = fused ? fz.pos[b] : 0;
+  const bool persist = fused && (fz.keep == nullptr || fz.keep[b] != 0);
   int kps = (len + n_split - 1) / n_split;
   kps = ((kps + AD_TK - 1) / AD_TK) * AD_TK;
   const int k0 = split * kps;
   const int k1 = min(len, k0 + kps);
   const int n_keys = max(k1 - k0, 0);
   const int n_tiles = (n_keys + AD_TK - 1) / AD_TK;
-  const bool fused = fz.partial != nullptr;
   const bf16* kbase = k_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
   const bf16* vbase = v_arena + (((int64_t)b * heads + h) * cap + k0) * AD_HD;
   // The cached length is known now: every remaining K/V tile that still has a free ring stage goes out BEFORE the QKV reduce +
@@ -124,6 +128,11 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
       const int H = heads * AD_HD;
       const int64_t slice = (int64_t)B * 3 * H;
       const float* base = fz.partial + (int64_t)b * 3 * H + (int64_t)item * H + h * AD_HD + d;
+      float c = 1.f, sn = 0.f;
+      if (item < 2) {  // issued before the slice loads are consumed: both latencies overlap
+        c = bf2f(fz.cos_t[(int64_t)pos_b * AD_HD + d]);
+        sn = bf2f(fz.sin_t[(int64_t)pos_b * AD_HD + d]);
+      }
       float x1 = 0.f, x2 = 0.f;
       for (int s0 = 0; s0 < fz.n_slices; s0 += 8) {
         float t1[8], t2[8];
@@ -142,11 +151,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
       }
       x1 = rbf(x1);
       x2 = rbf(x2);
-      const bool persist = fz.keep == nullptr || fz.keep[b] != 0;
       const int64_t arow = (((int64_t)b * heads + h) * cap + len) * AD_HD;
       if (item < 2) {
-        const int p = fz.pos[b];
-        const float c = bf2f(fz.cos_t[(int64_t)p * AD_HD + d]), sn = bf2f(fz.sin_t[(int64_t)p * AD_HD + d]);
         const float o1 = rbf(rbf(x1 * c) + rbf(-x2 * sn));
         const float o2 = rbf(rbf(x2 * c) + rbf(x1 * sn));
         if (item == 0) {
