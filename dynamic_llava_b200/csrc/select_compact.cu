@@ -1,5 +1,6 @@
 // K1: vision-token selection + gather/compact in ONE kernel
-// (dynamic_modeling_llama.py:1867, :1897-1994): score = log_softmax(logits)[..., 0] (bf16 rounding),
+// (dynamic_modeling_llama.py:1867, :1897-1994): score = log_softmax(logits)[..., 0] (fp32 math, ONE rounding to bf16: torch's
+// CUDA kernel; torch's CPU bf16 path rounds intermediates and is one ulp off on ~45 % of the scores),
 // keep = ascending indices of the k best scores, hidden' = [left | image[keep] | right], RoPE positions stay the
 // ORIGINAL (pre-drop) positions, and a CSR header (cu_seqlens) describes the packed result.
 //

@@ -188,19 +188,34 @@ def test_greedy_next_and_eos(L):
 
 # ---------------------------------------------------------------------------------------------- K1 select + compact
 def _tie_aware_same(keep_gpu, logits, k):
-    score = F.log_softmax(logits, dim=-1)[:, :, 0].float()
+    """Two checks of the selection.
+    (1) EXACT against the kernel's stated semantics = torch-CUDA's bf16 log_softmax (fp32 accumulate, ONE rounding to bf16), stable
+        descending order: the k best (score, lower index first), returned ascending.
+    (2) Against the CPU oracle's scores.  torch-CPU's bf16 log_softmax rounds intermediates and lands one bf16 ulp away from the
+        singly-rounded value on ~45 % of the entries (checked on these inputs), so that comparison is tie- AND ulp-aware: everything
+        clearly above the k-th score must be kept, nothing clearly below it may be."""
+    s1 = F.log_softmax(logits.float(), dim=-1)[:, :, 0].to(BF).float()
+    s_cpu = F.log_softmax(logits, dim=-1)[:, :, 0].float()
+    n = logits.shape[1]
     for b in range(logits.shape[0]):
-        srt = torch.sort(score[b], descending=True).values
-        kth = srt[k - 1]
-        must = set(torch.nonzero(score[b] > kth).flatten().tolist())
-        may = set(torch.nonzero(score[b] >= kth).flatten().tolist())
-        got = set(keep_gpu[b].tolist())
-        assert len(got) == k and must <= got <= may, f"sample {b}: selection differs beyond k-th-score ties"
-        assert keep_gpu[b].tolist() == sorted(got)
+        got = keep_gpu[b].tolist()
+        assert got == sorted(set(got)) and len(got) == k
+        order = sorted(range(n), key=lambda i: (-s1[b, i].item(), i))
+        want = sorted(order[:k])
+        if got != want:  # expf/logf may differ from libm by an ulp exactly at a bf16 rounding boundary: allow a swap among k-th-score ties only
+            kth = s1[b, order[k - 1]].item() if k > 0 else float("inf")
+            assert set(got) ^ set(want) <= {i for i in range(n) if abs(s1[b, i].item() - kth) <= abs(kth) * 2 ** -7}, f"sample {b}"
+        if k > 0:
+            kth = torch.sort(s_cpu[b], descending=True).values[k - 1].item()
+            band = abs(kth) * 2 ** -6  # two bf16 ulps
+            must = set(torch.nonzero(s_cpu[b] > kth + band).flatten().tolist())
+            may = set(torch.nonzero(s_cpu[b] >= kth - band).flatten().tolist())
+            assert must <= set(got) <= may, f"sample {b}: selection differs from the CPU oracle beyond ties / one bf16 ulp"
     return True
 
 
-@pytest.mark.parametrize("B,T,n_img,H,rate", [(2, 12, 16, 256, 0.5), (8, 32, 576, 4096, 0.2), (3, 32, 576, 512, 0.1), (2, 32, 576, 512, 1.0)])
+@pytest.mark.parametrize("B,T,n_img,H,rate", [(2, 12, 16, 256, 0.5), (8, 32, 576, 4096, 0.2), (3, 32, 576, 512, 0.1), (2, 32, 576, 512, 1.0),
+                                              (4, 1473, 576, 5120, 0.2), (16, 32, 576, 4096, 0.5)])  # + config 4 per GPU, config 5 (keep 0.5)
 def test_select_compact(L, B, T, n_img, H, rate):
     s0 = 5
     Pn = T - 1 + n_img
@@ -558,6 +573,32 @@ def test_integration_stub_sdpa_prefill(L, B, nh, Lq, Lk):
     mask = torch.ones(Lq, Lk, dtype=torch.bool, device=DEV).tril(diagonal=Lk - Lq)
     ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=mask)
     assert (got - ref).abs().max().item() < 2e-2
+
+
+def test_attn_prefill_full_size_config4_two_implementations_agree(L):
+    """BASELINE config 4 per GPU at full size (13B: 40 heads, B=4, L=2048 and the post-compaction L=1587): too big for the fp32
+    reference loop, so the persistent kernel is checked against the independent non-persistent tcgen05 kernel (different tiling,
+    schedule and epilogue) and against the size-independent row property softmax-weights-sum-to-one (V = 1 -> O = 1)."""
+    nh, hd, B = 40, 128, 4
+    H = nh * hd
+    for Lq in (2048, 1587):
+        cap, N = Lq + 3, B * Lq
+        g = torch.Generator(device=DEV).manual_seed(Lq)
+        qkv = torch.randn(N, 3 * H, device=DEV, dtype=BF, generator=g)
+        K = torch.randn(B, nh, cap, hd, device=DEV, dtype=BF, generator=g)
+        V = torch.randn(B, nh, cap, hd, device=DEV, dtype=BF, generator=g)
+        cu = torch.arange(0, (B + 1) * Lq, Lq, device=DEV, dtype=torch.int32)
+        past = torch.zeros(B, device=DEV, dtype=torch.int32)
+        o2, o4 = torch.empty(N, H, device=DEV, dtype=BF), torch.empty(N, H, device=DEV, dtype=BF)
+        sc = 1.0 / math.sqrt(hd)
+        L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(o2), H, P(cu), P(past), N, B, nh, cap, Lq, sc, ST())
+        L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o4), H, P(cu), P(past), N, B, nh, cap, Lq, sc, 0, ST())
+        torch.cuda.synchronize()
+        assert (o2.float() - o4.float()).abs().max().item() < 2e-2
+        ones = torch.ones_like(V)
+        L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(ones), P(o4), H, P(cu), P(past), N, B, nh, cap, Lq, sc, 1, ST())
+        torch.cuda.synchronize()
+        assert (o4.float() - 1.0).abs().max().item() < 1e-2
 
 
 def test_attn_prefill_tc4_more_than_63_samples(L):
