@@ -29,6 +29,7 @@ SOURCES = [
     "gemm_tc.cu",
     "decode_fused.cu",
     "predictor_ops.cu",
+    "sample.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -59,6 +59,7 @@ class Session:
         self.tp_logits = e(B, 2)
         self.tp_partial = e(8 * B * D, dtype=torch.float32)  # split-K slices of the text predictor's first Linear (own buffer: it
         # runs on a side stream next to the QKV GEMM, which owns `partial`)
+        self.rng_seed = torch.zeros(1, device=dev, dtype=torch.int64)  # per-generate() seed of dl_sample_next (device: graph-replayable)
         self.forced_buf = torch.zeros(max(max_new, 1), B, device=dev, dtype=torch.uint8)
         self.forced = None  # uint8 [n_steps, B] (forced_buf when a forced decision stream is in use)
         self.attn_ws = None
@@ -580,6 +581,13 @@ class Engine:
         a.host_ub_hi += 1
         if keep is not None:
             a.hi_exact = False
+
+    def sample(self, sess: Session, logits, eos, pad, temperature, top_k, top_p):
+        """HF `sample` step (temperature -> top-k -> top-p -> multinomial) on the device; same bookkeeping as greedy()."""
+        self.L.sample_next(_p(logits), sess.B, logits.shape[-1], float(temperature), int(top_k), float(top_p), _p(sess.rng_seed),
+                           _p(sess.next_ids), _p(sess.tokens), sess.tokens.shape[1], _p(sess.arena.step), _p(sess.finished),
+                           -1 if eos is None else int(eos), int(pad), None, _stream())
+        self.launches += 1
 
     def greedy(self, sess: Session, logits, eos, pad):
         self.L.greedy_next(_p(logits), sess.B, logits.shape[-1], _p(sess.next_ids), _p(sess.tokens), sess.tokens.shape[1],

@@ -2,7 +2,7 @@
 (llava/model/language_model/dynamic_llava_llama.py:39-173) on top of the B200 engine.
 
 Kept from the reference: `forward(...)` signature and `CausalLMOutputWithPast`-shaped result with fp32 logits and a
-legacy-tuple `past_key_values`; `generate(inputs, images, image_sizes, **kwargs)` (greedy); the
+legacy-tuple `past_key_values`; `generate(inputs, images, image_sizes, **kwargs)` (greedy and HF `sample`); the
 `prepare_inputs_labels_for_multimodal` return shape; `model.model.image_score_predictor` & friends as hookable
 modules; the live, mutable `config.sparse_config` dict that callers edit at run time
 (llava/dynamic_eval/bench_test/dynamic_llava_image_time_and_mem.py:63-65); the state-dict key names.
@@ -300,8 +300,22 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         kwargs.pop("input_embeds_indices", None)
         if "inputs_embeds" in kwargs:
             raise NotImplementedError("`inputs_embeds` is not supported")
-        if kwargs.get("do_sample", False) or kwargs.get("num_beams", 1) != 1:
-            raise NotImplementedError("sampling / beam search are SURVEY.md §8f 'next' rows; greedy only")
+        if kwargs.get("num_beams", 1) not in (1, None):
+            raise NotImplementedError("beam search is a SURVEY.md §8f 'next' row; num_beams must be 1")
+        sampling = None  # (temperature, top_k, top_p): HF 4.37.2 `sample` (model_vqa_loader.py:169-172: do_sample = temperature > 0)
+        if kwargs.get("do_sample", False):
+            temperature = kwargs.get("temperature", None)
+            temperature = 1.0 if temperature is None else float(temperature)
+            if temperature <= 0:
+                raise ValueError("`temperature` has to be a strictly positive float when do_sample=True")
+            gc = getattr(self, "generation_config", None)
+            top_k = kwargs.get("top_k", getattr(gc, "top_k", 50) if gc is not None else 50)  # GenerationConfig default
+            top_k = 0 if top_k is None else int(top_k)
+            top_p = kwargs.get("top_p", None)
+            top_p = 1.0 if top_p is None else float(top_p)
+            if top_k > 1024 or (top_k == 0 and top_p < 1.0):
+                raise NotImplementedError("top_k must be in [1, 1024] when top_p < 1 (dl_sample_next keeps <= 1024 candidates)")
+            sampling = (temperature, top_k, top_p)
         max_new = kwargs.get("max_new_tokens", 20)
         min_new = kwargs.get("min_new_tokens", 0) or 0
         eos = kwargs.get("eos_token_id", self.config.eos_token_id)
@@ -343,12 +357,22 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             sess.forced = sess.forced_buf
         quirk = bool(getattr(self.config, "reference_batched_quirk", False)) and B > 1
         eos_k = None if eos is None else int(eos)
+        if sampling is not None:
+            seed = kwargs.get("seed", None)  # reproducible under torch.manual_seed, like HF's torch.multinomial draw
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
+            sess.rng_seed.fill_(seed)
+
+        def pick(lg, eos_):
+            if sampling is None:
+                eng.greedy(sess, lg, eos_, pad)
+            else:
+                eng.sample(sess, lg, eos_, pad, *sampling)
         logits = eng.prefill(sess, embeds, indices, forced_keep=forced_keep)
-        eng.greedy(sess, logits, eos_k if min_new <= 0 else None, pad)
+        pick(logits, eos_k if min_new <= 0 else None)
         eng.L.kv_advance(None, None, a.step.data_ptr(), None, 0, B, 0, 0, 0, torch.cuda.current_stream().cuda_stream)  # step += 1
         n_done = 1
         graph = None
-        gkey = (use_dec, quirk, eos_k, pad, None if sess.forced is None else sess.forced.data_ptr())
+        gkey = (use_dec, quirk, eos_k, pad, None if sess.forced is None else sess.forced.data_ptr(), sampling)
         while n_done < max_new:
             eos_now = eos_k if n_done >= min_new else None
             if use_graph and sess.graph is not None and sess.graph_key == gkey + (eos_now,):
@@ -360,7 +384,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             else:
                 def step():
                     keep = eng.decode_layers(sess, use_dec, quirk)
-                    eng.greedy(sess, sess.logits, eos_now, pad)
+                    pick(sess.logits, eos_now)
                     eng.decode_advance(sess, keep)
                 if use_graph and n_done >= 2:
                     # the first decode step ran eagerly (function attributes, workspaces); capture the rest once

@@ -173,6 +173,15 @@ int dl_text_decision(const float* partial, int splits, int B, int D, const void*
 int dl_greedy_next(const void* logits, int B, int V, int64_t* next_ids, int64_t* tokens_out, int out_stride,
                    const int32_t* step_counter, int32_t* finished, int eos_token_id, int pad_token_id, cudaStream_t stream);
 
+/* HF 4.37.2 GenerationMixin.sample step (transformers, unvendored; reached from llava/dynamic_eval/model_vqa_loader.py:162-175 with
+ * do_sample = temperature > 0): scores = logits / temperature -> top-k (ties at the k-th value kept) -> top-p (ascending cumulative
+ * softmax <= 1 - top_p removed, top-1 always kept) -> multinomial draw (Philox4x32-10, key = seed[0], counter = (step, row)); finished
+ * rows emit pad, finished |= (token == eos).  logits bf16 [B,V], V <= 32768; seed int64[1], step_counter int32[1] on the device;
+ * probs_out fp32 [B,V] or NULL (the distribution drawn from).  top_k in [0, 1024]; top_k == 0 requires top_p >= 1. */
+int dl_sample_next(const void* logits, int B, int V, float temperature, int top_k, float top_p, const int64_t* seed,
+                   int64_t* next_ids, int64_t* tokens_out, int out_stride, const int32_t* step_counter, int32_t* finished,
+                   int eos_token_id, int pad_token_id, float* probs_out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

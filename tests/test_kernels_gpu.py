@@ -266,6 +266,99 @@ def test_select_compact_forced_and_ties(L):
     assert torch.equal(out.cpu()[:, s0:s0 + k], hid[:, s0:s0 + n_img].gather(1, forced[..., None].expand(B, k, H)))
 
 
+# ---------------------------------------------------------------------------------------------- sampling
+def _hf_warped_probs(logits, temperature, top_k, top_p):
+    """torch restatement of transformers 4.37.2 TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper -> softmax
+    (logits_process.py; min_tokens_to_keep = 1), on the fp32 logits the reference hands to generate()."""
+    scores = logits.float() / temperature
+    if top_k > 0:
+        kth = torch.topk(scores, min(top_k, scores.shape[-1]))[0][..., -1, None]
+        scores = scores.masked_fill(scores < kth, float("-inf"))
+    if top_p < 1.0:
+        srt, idx = torch.sort(scores, descending=False)
+        cum = srt.softmax(dim=-1).cumsum(dim=-1)
+        rem = cum <= (1 - top_p)
+        rem[..., -1:] = False
+        scores = scores.masked_fill(rem.scatter(1, idx, rem), float("-inf"))
+    return scores.softmax(dim=-1)
+
+
+def _sample(L, logits, step, seed, temperature, top_k, top_p, want_probs=True, eos=-1):
+    B, V = logits.shape
+    lg = logits.to(DEV)
+    nxt = torch.full((B,), -7, device=DEV, dtype=torch.int64)
+    toks = torch.full((B, 64), -7, device=DEV, dtype=torch.int64)
+    stepc = torch.tensor([step], device=DEV, dtype=torch.int32)
+    fin = torch.zeros(B, device=DEV, dtype=torch.int32)
+    sd = torch.tensor([seed], device=DEV, dtype=torch.int64)
+    probs = torch.full((B, V), float("nan"), device=DEV, dtype=torch.float32) if want_probs else None
+    L.sample_next(P(lg), B, V, temperature, top_k, top_p, P(sd), P(nxt), P(toks), 64, P(stepc), P(fin), eos, 0, P(probs), ST())
+    torch.cuda.synchronize()
+    assert torch.equal(toks[:, step], nxt)
+    return nxt.cpu(), (probs.cpu() if want_probs else None)
+
+
+@pytest.mark.parametrize("temperature,top_k,top_p", [(0.7, 50, 0.9), (1.0, 0, 1.0), (0.2, 50, 1.0), (1.3, 1000, 0.5), (1.0, 1, 1.0), (2.0, 7, 0.3)])
+def test_sample_next_distribution_matches_hf_warpers(L, temperature, top_k, top_p):
+    """the distribution the token is drawn from == temperature / top-k / top-p warpers + softmax of HF 4.37.2, restated in torch"""
+    logits = rnd(4, 32000, seed=160, scale=3.0)
+    tok, probs = _sample(L, logits, 3, 1234, temperature, top_k, top_p)
+    ref = _hf_warped_probs(logits, temperature, top_k, top_p)
+    assert torch.isfinite(probs).all() and (probs.sum(-1) - 1).abs().max() < 1e-4
+    # bf16 logits tie a lot and HF's ascending torch.sort breaks ties arbitrarily, so WHICH of several equal-score tokens falls under
+    # the top-p cut is not defined: the sorted probability vectors must agree, and tokens on which the supports differ must be exact
+    # ties (same logit) of a token at the edge of the support
+    assert (probs.sort(-1, descending=True).values - ref.sort(-1, descending=True).values).abs().max().item() < 2e-5
+    lf = logits.float()
+    for r in range(logits.shape[0]):
+        sup_k, sup_r = probs[r] > 0, ref[r] > 0
+        assert int(sup_k.sum()) == int(sup_r.sum())
+        diff = (sup_k ^ sup_r).nonzero().flatten()
+        if len(diff):
+            edge = lf[r][sup_r].min()
+            assert (lf[r][diff] == edge).all(), (r, diff.tolist())
+    assert (probs.gather(1, tok[:, None]) > 0).all()
+    if top_k == 1:
+        assert torch.equal(tok, logits.float().argmax(-1))
+
+
+def test_sample_next_frequencies_and_determinism(L):
+    """10 240 draws (256 identical rows x 40 steps) follow the warped distribution; the stream is a pure function of (seed, step, row)"""
+    g = torch.Generator().manual_seed(161)
+    row = (torch.randn(1, 1000, generator=g) * 2.0).to(BF)
+    logits = row.repeat(256, 1)
+    ref = _hf_warped_probs(row, 0.8, 20, 0.95)[0]
+    counts = torch.zeros(1000)
+    draws = []
+    for step in range(40):
+        tok, _ = _sample(L, logits, step, 99, 0.8, 20, 0.95, want_probs=False)
+        draws.append(tok)
+        counts += torch.bincount(tok, minlength=1000).float()
+    n = 256 * 40
+    assert counts[ref == 0].sum() == 0
+    sigma = torch.sqrt(n * ref * (1 - ref)).clamp_min(1.0)
+    assert ((counts - n * ref).abs() / sigma).max().item() < 5.0
+    again, _ = _sample(L, logits, 7, 99, 0.8, 20, 0.95, want_probs=False)
+    assert torch.equal(again, draws[7])
+    other, _ = _sample(L, logits, 7, 100, 0.8, 20, 0.95, want_probs=False)
+    assert not torch.equal(other, draws[7])
+    assert len(set(draws[7].tolist())) > 3  # rows draw independently
+
+
+def test_sample_next_eos_bookkeeping(L):
+    logits = torch.full((3, 4096), -20.0, dtype=BF)
+    logits[:, 2] = 20.0  # every row draws token 2 == eos
+    lg = logits.to(DEV)
+    nxt = torch.zeros(3, device=DEV, dtype=torch.int64)
+    toks = torch.zeros(3, 8, device=DEV, dtype=torch.int64)
+    stepc = torch.tensor([1], device=DEV, dtype=torch.int32)
+    fin = torch.tensor([0, 1, 0], device=DEV, dtype=torch.int32)
+    sd = torch.tensor([5], device=DEV, dtype=torch.int64)
+    L.sample_next(P(lg), 3, 4096, 1.0, 50, 1.0, P(sd), P(nxt), P(toks), 8, P(stepc), P(fin), 2, 9, None, ST())
+    torch.cuda.synchronize()
+    assert nxt.tolist() == [2, 9, 2] and fin.tolist() == [1, 1, 1] and toks[:, 1].tolist() == [2, 9, 2]
+
+
 # ---------------------------------------------------------------------------------------------- K4+K5 rope + append
 def test_rope_append_prefill_and_decode(L):
     B, Lq, nh, hd, cap = 2, 9, 2, 128, 32

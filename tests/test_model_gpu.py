@@ -311,7 +311,7 @@ def test_generate_eos_stops_early_and_text_only_generate():
     lg, past = O.llama_forward(sd16, cfg, input_ids=txt)
     assert t.shape == (1, 5) and int(t[0, 0]) == int(lg[0, -1].argmax())
     with pytest.raises(NotImplementedError):
-        model.generate(ids, images=pix, do_sample=True, max_new_tokens=2)
+        model.generate(ids, images=pix, num_beams=4, max_new_tokens=2)
     with pytest.raises(NotImplementedError):
         model.generate(ids, images=pix, num_beams=2, max_new_tokens=2)
 
@@ -427,3 +427,25 @@ def test_full_size_13b_config4_prefill_properties():
     assert torch.equal(lens_half, lens[:, :2])
     del model
     torch.cuda.empty_cache()
+
+
+def test_generate_do_sample():
+    """HF `sample` path of generate() (model_vqa_loader.py:162-175 with its default --temperature 0.2): reproducible per seed, CUDA-graph
+    replay == eager loop, top_k = 1 degenerates to greedy, beams still refused."""
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b2_forced", out_pred=True)
+    kw = dict(images=pix, max_new_tokens=10, eos_token_id=None)
+    a = model.generate(ids, do_sample=True, temperature=0.2, top_p=None, num_beams=1, seed=11, **kw).cpu()
+    b = model.generate(ids, do_sample=True, temperature=0.2, top_p=None, num_beams=1, seed=11, **kw).cpu()
+    c = model.generate(ids, do_sample=True, temperature=0.2, top_p=None, num_beams=1, seed=11, use_cuda_graph=False, **kw).cpu()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert a.shape == (g["B"], 10) and int(a.min()) >= 0 and int(a.max()) < cfg["vocab_size"]
+    hot = model.generate(ids, do_sample=True, temperature=5.0, top_k=0, seed=12, **kw).cpu()
+    assert not torch.equal(hot, a)
+    greedy = model.generate(ids, do_sample=False, **kw).cpu()
+    assert torch.equal(model.generate(ids, do_sample=True, temperature=0.7, top_k=1, seed=3, **kw).cpu(), greedy)
+    torch.manual_seed(5)
+    x = model.generate(ids, do_sample=True, temperature=1.0, top_p=0.9, **kw).cpu()
+    torch.manual_seed(5)
+    assert torch.equal(x, model.generate(ids, do_sample=True, temperature=1.0, top_p=0.9, **kw).cpu())
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, num_beams=3, **kw)
