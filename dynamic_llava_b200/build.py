@@ -21,6 +21,7 @@ SOURCES = [
     "elementwise.cu",
     "select_compact.cu",
     "rope_append.cu",
+    "kv_turn.cu",
     "attn_decode.cu",
     "attn_prefill_mma.cu",
     "attn_prefill_tc2.cu",

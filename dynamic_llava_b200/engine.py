@@ -449,6 +449,36 @@ class Engine:
                         d[key][1] -= drop
                 if record is not None:
                     record.update(vision_logits=logits, keep_index=keep, position_ids=pos.view(B, Pp))
+            if sc["use_text_predictor"] and sc["use_instruct_predictor"] and l == SL and have_idx:
+                # prefill-time instruction dropping (:2261-2375): tokens of the last instruct span (its final token excluded)
+                # stay only where the instruct predictor's logit0 > logit1
+                assert B == 1, "Using text predictor must keep the batch size to 1"
+                a0, b0 = indices[0]["last_instruct"][0], indices[0]["last_instruct"][1] - 1
+                if b0 < a0:
+                    raise NotImplementedError("empty instruct span (the <image> placeholder is the last prompt token)")
+                if b0 > a0:
+                    n_span = b0 - a0
+                    lg = m.instruct_score_predictor(x.view(B, Lq, H)[:, a0:b0, :]).contiguous()  # via __call__: hooks fire
+                    dec = torch.empty(n_span, device=self.device, dtype=torch.uint8)
+                    self.L.turn_decision(_p(lg), None, _p(dec), 1, n_span, 0, _stream())
+                    keep_i = dec.nonzero().flatten()  # one host sync for the new length, like the reference's torch.where (:2280)
+                    ar = torch.arange(Lq, device=self.device, dtype=torch.int64)
+                    idx = torch.cat([ar[:a0], keep_i + a0, ar[b0:]]).contiguous()
+                    Ln = idx.numel()
+                    x_new = torch.empty(Ln, H, device=self.device, dtype=self.dtype)
+                    pos_new = torch.empty(Ln, device=self.device, dtype=torch.int32)
+                    self.L.gather_rows_pos(_p(x), _p(pos), _p(idx), _p(x_new), _p(pos_new), Ln, H, _stream())
+                    self.launches += 2
+                    drop = Lq - Ln
+                    x, pos, Lq = x_new, pos_new, Ln
+                    cu = torch.tensor([0, Ln], device=self.device, dtype=torch.int32)
+                    for d in indices:  # :2364-2375
+                        d["instruct"][1] -= drop
+                        d["last_instruct"][1] -= drop
+                        d["answer"][0] -= drop
+                        d["answer"][1] -= drop
+                    if record is not None:
+                        record.update(instruct_logits=lg, instruct_keep_index=keep_i.view(1, -1), position_ids=pos.view(B, Lq))
             if record is not None:
                 record.setdefault("layer_inputs", []).append(x.view(B, Lq, H).clone())
             x = self._prefill_layer(l, x, pos, cu, sess, B, Lq)
@@ -466,29 +496,47 @@ class Engine:
         return F.linear(xn, self.model.lm_head.weight, out=None)
 
     @torch.no_grad()
-    def continue_prefill(self, sess: Session, input_ids):
-        """q_len > 1 over an existing cache (a new user turn): DynamicLlamaModel.forward with a past and
-        `use_instruct_predictor=False` (dynamic_modeling_llama.py:1714-1722 positions from the layer-0 length, per-layer causal
-        mask offset by that layer's cached length :1791-1818, plain append in every layer :1078-1083).  Per-sample cache
-        lengths may differ (earlier dropped tokens); each sample's new keys land right after ITS cached keys."""
+    def continue_prefill(self, sess: Session, input_ids, record=None):
+        """q_len > 1 over an existing cache (a new user turn): DynamicLlamaModel.forward with a past
+        (dynamic_modeling_llama.py:1714-1722 positions from the layer-0 length, per-layer causal mask offset by that layer's cached
+        length :1791-1818).  Per-sample cache lengths may differ (earlier dropped tokens); each sample's new keys land right
+        after ITS cached keys.  `use_instruct_predictor=False`: plain append in every layer (:1078-1083).  With the instruct
+        predictor (:2506-2521) every new token is attended to (cache_utils.py:256-268) but layers >= sparse_layer persist only
+        the tokens whose logit0 > logit1, the last one always (cache_utils.py:165-241): the new rows are compacted in place
+        after the layer's attention and the per-sample lengths advance by the kept counts."""
         self._check_packed()
-        c = self.cfg
+        c, sc = self.cfg, self.cfg.sparse_config
         m = self.model.model
         a = sess.arena
         B, Tq = input_ids.shape
-        H = c.hidden_size
+        H, nh = c.hidden_size, c.num_attention_heads
+        SL = sc["sparse_layer"]
         ids = input_ids.to(self.device, torch.int64).contiguous()
         x = torch.empty(B * Tq, H, device=self.device, dtype=self.dtype)
         self.L.embed_rows(_p(ids), _p(m.embed_tokens.weight), _p(x), B * Tq, H, _stream())
         self.launches += 1
         pos = (a.pos.view(B, 1) + torch.arange(Tq, device=self.device, dtype=torch.int32).view(1, Tq)).reshape(-1).contiguous()
         cu = torch.arange(0, (B + 1) * Tq, Tq, device=self.device, dtype=torch.int32)
+        keep = None
         for l in range(c.num_hidden_layers):
+            if l == SL and sc["use_text_predictor"] and sc["use_instruct_predictor"]:
+                lg = m.instruct_score_predictor(x.view(B, Tq, H)).contiguous()  # via __call__: forward hooks fire
+                keep = torch.empty(B * Tq, device=self.device, dtype=torch.uint8)
+                self.L.turn_decision(_p(lg), None, _p(keep), B, Tq, 1, _stream())
+                self.launches += 1
+                if record is not None:
+                    record.update(instruct_logits=lg, text_decision=keep.view(B, Tq).bool())
             x = self._prefill_layer(l, x, pos, cu, sess, B, Tq)
-        self.L.kv_advance(_p(a.kv_len), _p(a.pos), None, None, c.num_hidden_layers, B, c.sparse_config["sparse_layer"], Tq, Tq, _stream())
+            if keep is not None:
+                K, V, cap = a.layer(l)
+                self.L.kv_compact_turn(_p(K), _p(V), _p(a.kv_len[l]), _p(keep), Tq, B, nh, H // nh, cap, _stream())
+                self.launches += 1
+        self.L.kv_advance_turn(_p(a.kv_len), _p(a.pos), _p(keep), c.num_hidden_layers, B, SL, Tq, _stream())
         self.launches += 1
         a.host_len_lo += Tq
         a.host_ub_hi += Tq
+        if keep is not None:
+            a.hi_exact = False
         xn = self.rmsnorm(x, m.norm.weight, c.rms_norm_eps)
         return F.linear(xn, self.model.lm_head.weight).view(B, Tq, -1)
 

@@ -244,9 +244,6 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                 inputs_embeds = torch.empty(*ids.shape, self.config.hidden_size, device=self.device, dtype=self.dtype)
                 eng.L.embed_rows(ids.contiguous().data_ptr(), self.model.embed_tokens.weight.data_ptr(), inputs_embeds.data_ptr(),
                                  ids.numel(), self.config.hidden_size, torch.cuda.current_stream().cuda_stream)
-            if sc["use_text_predictor"] and sc["use_instruct_predictor"] and input_embeds_indices is not None:
-                raise NotImplementedError("instruct predictor (prefill-time instruction dropping) is a SURVEY.md §8f 'next' row; "
-                                          "set sparse_config['use_instruct_predictor']=False as the reference's scripts do (README.md:110)")
             B, P, _ = inputs_embeds.shape
             k_drop = 0
             if sc["use_vision_predictor"] and input_embeds_indices is not None and len(input_embeds_indices) == B:
@@ -271,10 +268,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             sess.graph = None
         if n_in > 1:
             # a new user turn over the existing cache (model_lvis_multi_round_for_meteor.py:150-185)
-            if sc["use_text_predictor"] and sc["use_instruct_predictor"]:
-                raise NotImplementedError("instruct predictor on a new turn (dynamic_modeling_llama.py:2506-2521) is a SURVEY.md §8f "
-                                          "'next' row; the reference's scripts run with use_instruct_predictor=False (README.md:110)")
-            logits = eng.continue_prefill(sess, ids)
+            logits = eng.continue_prefill(sess, ids, record=record)
             return CausalLMOutputWithPast(logits=logits.float(), past_key_values=LegacyPastView(a, sess))
         sess.next_ids.copy_(ids.reshape(-1).to(self.device, torch.int64))
         use_dec = bool(sc["use_text_predictor"] and sc["use_output_text_predictor"])
@@ -340,8 +334,6 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             eng.L.embed_rows(inputs.contiguous().data_ptr(), self.model.embed_tokens.weight.data_ptr(), embeds.data_ptr(),
                              inputs.numel(), self.config.hidden_size, torch.cuda.current_stream().cuda_stream)
             indices = None
-        if sc["use_text_predictor"] and sc["use_instruct_predictor"] and indices is not None:
-            raise NotImplementedError("instruct predictor is a SURVEY.md §8f 'next' row; set use_instruct_predictor=False")
         B, P, _ = embeds.shape
         k_drop = 0
         if sc["use_vision_predictor"] and indices is not None and len(indices) == B:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DL_B200_ABI_VERSION 2  /* 2: persistent attention (tc4) entry points added, v1 tcgen05 attention removed */
+#define DL_B200_ABI_VERSION 3  /* 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points */
 
 int dl_version(void);
 const char* dl_last_error_string(void);
@@ -181,6 +181,23 @@ int dl_greedy_next(const void* logits, int B, int V, int64_t* next_ids, int64_t*
 int dl_sample_next(const void* logits, int B, int V, float temperature, int top_k, float top_p, const int64_t* seed,
                    int64_t* next_ids, int64_t* tokens_out, int out_stride, const int32_t* step_counter, int32_t* finished,
                    int eos_token_id, int pad_token_id, float* probs_out, cudaStream_t stream);
+
+/* ---- instruct predictor (sparse_config["use_instruct_predictor"]), DML:2261-2375 (prefill drop), :2506-2521 (new turn),
+ * CU:165-241 (per-sample persistence of the kept rows) ---------------------------------------------------------------- */
+/* keep[n] = forced ? forced[n] : logit0 > logit1 over logits bf16 [B*Tq, 2]; force_last: the last token of every sample is
+ * kept (DML:2520).  logits or forced may be NULL, not both. */
+int dl_turn_decision(const void* logits, const uint8_t* forced, uint8_t* keep, int B, int Tq, int force_last, cudaStream_t stream);
+/* After a new-turn layer's attention: of the Tq rows dl_rope_append wrote at slots [kv_len[b], kv_len[b]+Tq) of one layer's
+ * arenas [B, heads, cap, hd], only those with keep[b*Tq + j] stay, moved left in place.  kv_len int32 [B] of that layer. */
+int dl_kv_compact_turn(void* k_arena, void* v_arena, const int32_t* kv_len, const uint8_t* keep, int Tq, int B, int heads,
+                       int head_dim, int cap, cudaStream_t stream);
+/* kv_len int32 [L,B]: layers < sparse_layer += Tq, layers >= sparse_layer += sum_j keep[b*Tq + j] (keep NULL: Tq);
+ * pos[b] += Tq (NULL allowed). */
+int dl_kv_advance_turn(int32_t* kv_len, int32_t* pos, const uint8_t* keep, int L, int B, int sparse_layer, int Tq,
+                       cudaStream_t stream);
+/* out[i] = x[idx[i]] (rows of H bf16), pos_out[i] = pos[idx[i]]; idx int64 [n] on the device; pos/pos_out both NULL or both set. */
+int dl_gather_rows_pos(const void* x, const int32_t* pos, const int64_t* idx, void* out, int32_t* pos_out, int n, int H,
+                       cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -241,12 +241,13 @@ def decoder_layer(sd, cfg, i, x, position_ids, cache, text_decision, cos, sin) -
 def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = None, inputs_embeds: Optional[Tensor] = None,
                   position_ids: Optional[Tensor] = None, past=None, indices: Optional[List[dict]] = None,
                   forced_keep_index: Optional[Tensor] = None, forced_text_decision: Optional[Tensor] = None,
-                  record: Optional[dict] = None):
+                  forced_instruct: Optional[Tensor] = None, record: Optional[dict] = None):
     """DynamicLlamaModel.forward, eval + use_cache branches only (dynamic_modeling_llama.py:1656-2594), followed by
     lm_head + .float() (:2709-2710).  Returns (logits fp32 [B, Lq', V], legacy past tuple).
 
     `forced_keep_index` [B,k] / `forced_text_decision` [B,Lq] bool replace the predictors' own decisions
-    (parity "under the same predictor masks"); `record` (dict) receives intermediates."""
+    (parity "under the same predictor masks"); `forced_instruct` bool [span] (prefill) / [Lq] (new turn)
+    replaces the instruct predictor's `logit0 > logit1`; `record` (dict) receives intermediates."""
     sc = cfg["sparse_config"]
     if (input_ids is None) == (inputs_embeds is None):
         raise ValueError("You have to specify exactly one of input_ids or inputs_embeds")  # :1686-1695
@@ -295,7 +296,8 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
                 a, b_ = indices[0]["last_instruct"][0], indices[0]["last_instruct"][1] - 1
                 ih = x[:, a:b_, :]
                 il = text_predictor(sd, ih, "model.instruct_score_predictor.").reshape(B, -1, 2)
-                keep_i = torch.where(il[0, :, 0] > il[0, :, 1])[0].unsqueeze(0)
+                dec_i = il[0, :, 0] > il[0, :, 1] if forced_instruct is None else forced_instruct.reshape(-1)
+                keep_i = torch.where(dec_i)[0].unsqueeze(0)
                 x = torch.cat([x[:, :a, :], ih.gather(1, keep_i[..., None].expand(B, -1, x.shape[2])), x[:, b_:, :]], dim=1)
                 position_ids = torch.cat([position_ids[:, :a], position_ids[:, a:b_].gather(1, keep_i), position_ids[:, b_:]], dim=1)
                 drop = b_ - a - keep_i.shape[1]
@@ -305,7 +307,7 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
                     d["answer"][0] -= drop
                     d["answer"][1] -= drop
                 if record is not None:
-                    record.update(instruct_keep_index=keep_i)
+                    record.update(instruct_keep_index=keep_i, instruct_logits=il)
             elif past_len_i and x.shape[1] == 1 and sc["use_output_text_predictor"]:  # :2377-2391 decode decision
                 tl = text_predictor(sd, x).reshape(B, -1, 2)
                 text_decision = tl[:, :, 0] > tl[:, :, 1]
@@ -315,8 +317,10 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
                     text_decision = forced_text_decision
             elif past_len_i and x.shape[1] > 1 and sc["use_instruct_predictor"]:  # :2506-2521 new instruct turn
                 tl = text_predictor(sd, x, "model.instruct_score_predictor.").reshape(B, -1, 2)
-                text_decision = tl[:, :, 0] > tl[:, :, 1]
+                text_decision = tl[:, :, 0] > tl[:, :, 1] if forced_instruct is None else forced_instruct.reshape(B, -1).clone()
                 text_decision[:, -1:] = True
+                if record is not None:
+                    record.update(instruct_logits=tl)
         if record is not None:
             record["layer_inputs"].append(x)  # what the layer actually receives (post-compaction at i == SL)
         x = decoder_layer(sd, cfg, i, x, position_ids, cache, text_decision, cos, sin)  # :2541-2552
@@ -427,14 +431,14 @@ def prepare_multimodal(sd: StateDict, cfg: dict, input_ids: Tensor, pixels: Opti
 
 
 def model_forward(sd: StateDict, cfg: dict, input_ids: Tensor, *, images: Optional[Tensor] = None, past=None,
-                  forced_keep_index=None, forced_text_decision=None, record=None):
+                  forced_keep_index=None, forced_text_decision=None, forced_instruct=None, record=None):
     """DynamicLlavaLlamaForCausalLM.forward (language_model/dynamic_llava_llama.py:68-115)."""
     embeds, indices = prepare_multimodal(sd, cfg, input_ids, images)
     if embeds is None:
         return llama_forward(sd, cfg, input_ids=input_ids, past=past, forced_text_decision=forced_text_decision,
-                             record=record)
+                             forced_instruct=forced_instruct, record=record)
     return llama_forward(sd, cfg, inputs_embeds=embeds, past=past, indices=indices, forced_keep_index=forced_keep_index,
-                         forced_text_decision=forced_text_decision, record=record)
+                         forced_text_decision=forced_text_decision, forced_instruct=forced_instruct, record=record)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -518,17 +522,21 @@ def hf_greedy_generate(sd: StateDict, cfg: dict, input_ids: Tensor, images: Tens
 
 
 @torch.no_grad()
-def multiround_loop(sd, cfg, ids, pix, cont_ids):
+def multiround_loop(sd, cfg, ids, pix, cont_ids, forced_prefill=None, forced_turn=None, record=None):
     """prefill -> 3 greedy steps -> multi-token continuation (new user turn) -> 3 greedy steps: the call pattern of
-    llava/dynamic_eval/model_lvis_multi_round_for_meteor.py:150-185 (mirrors oracle/gen_golden.py:multiround_case)."""
+    llava/dynamic_eval/model_lvis_multi_round_for_meteor.py:150-185 (mirrors oracle/gen_golden.py:multiround_case and
+    :instruct_case; `forced_*` replace the instruct predictor's decisions, `record` gets its logits per call)."""
     logits, lens, toks = [], [], []
-    lg, past = model_forward(sd, cfg, ids, images=pix)
+    r0, r1 = {}, {}
+    lg, past = model_forward(sd, cfg, ids, images=pix, forced_instruct=forced_prefill, record=r0)
     for t in range(3):
         logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
         nxt = lg[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
         lg, past = model_forward(sd, cfg, nxt, past=past)
     logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
-    cont_lg, past = model_forward(sd, cfg, cont_ids, past=past)
+    cont_lg, past = model_forward(sd, cfg, cont_ids, past=past, forced_instruct=forced_turn, record=r1)
+    if record is not None:
+        record.update(instruct_logits_prefill=r0.get("instruct_logits"), instruct_logits_turn=r1.get("instruct_logits"))
     lens.append(torch.stack(list(past[1]), 0).clone())
     lg = cont_lg
     for t in range(3):

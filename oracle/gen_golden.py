@@ -212,7 +212,67 @@ def multiround_case(out_dir, scratch):
     print("multiround tokens", toks, "kv", res["kv_shapes"].tolist())
 
 
+@torch.no_grad()
+def instruct_case(out_dir, scratch):
+    """`use_instruct_predictor=True`: the prefill drops instruction tokens of the last instruct span
+    (dynamic_modeling_llama.py:2261-2375, B == 1 asserted) and a new user turn persists K/V only where the instruct
+    predictor says so, last token always (:2506-2521 + cache_utils.py:165-241).  Two variants in one fixture: the
+    predictor's own decisions ("natural") and +/-1 patterns injected through a forward hook ("forced")."""
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    cfg["sparse_config"]["use_instruct_predictor"] = True
+    sd = numpy_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd, torch.bfloat16, scratch)
+    T = 20
+    ids, pix = synthetic_inputs(cfg, 1, T, seed=1, dtype=torch.bfloat16)
+    cont, _ = synthetic_inputs(cfg, 1, 12, seed=5, dtype=torch.bfloat16)
+    cont = cont[:, 6:11].contiguous()
+    n_span = T - 1 - 5 - 1  # instruct tokens minus the last one (never dropped)
+    rng = torch.Generator().manual_seed(11)
+    forced = [torch.rand(n_span, generator=rng) < 0.6, torch.tensor([True, False, True, False, False])]
+    out_all = {}
+    for variant in ("natural", "forced"):
+        seen, it = [], iter(forced)
+
+        def hook(mod, args, out):
+            seen.append(out.detach().clone())
+            if variant == "natural":
+                return out
+            d = next(it)
+            z = torch.zeros_like(out)
+            z[..., 0] = torch.where(d.reshape(out.shape[:-1]), 1.0, -1.0).to(out.dtype)
+            return z
+        h = model.model.instruct_score_predictor.register_forward_hook(hook)
+        logits, lens, toks = [], [], []
+        snap = lambda o: torch.stack([x.clone() for x in o.past_key_values[1]], 0)
+        out = model(ids, images=pix, past_key_values=None)
+        for t in range(3):
+            logits.append(out.logits[:, -1].clone()); lens.append(snap(out))
+            nxt = out.logits[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
+            out = model(nxt, images=None, past_key_values=out.past_key_values)
+        logits.append(out.logits[:, -1].clone()); lens.append(snap(out))
+        out = model(cont, images=None, past_key_values=out.past_key_values)
+        cont_logits = out.logits.clone()
+        lens.append(snap(out))
+        for t in range(3):
+            nxt = out.logits[:, -1].argmax(-1).reshape(1, 1); toks.append(int(nxt))
+            out = model(nxt, images=None, past_key_values=out.past_key_values)
+            logits.append(out.logits[:, -1].clone()); lens.append(snap(out))
+        h.remove()
+        out_all[variant] = dict(tokens=toks, step_logits=torch.stack(logits, 0), cont_logits=cont_logits,
+                                true_len_hist=torch.stack(lens, 0), instruct_logits_prefill=seen[0], instruct_logits_turn=seen[1],
+                                kv_shapes=torch.tensor([k.shape[-2] for (k, v) in out.past_key_values[0]]))
+        print("instruct", variant, "tokens", toks, "kv", out_all[variant]["kv_shapes"].tolist(),
+              "prefill keep", (seen[0][0, :, 0] > seen[0][0, :, 1]).int().tolist() if variant == "natural" else forced[0].int().tolist())
+    res = dict(name="toy_bf16_b1_instruct", dtype="torch.bfloat16", B=1, T=T, weight_seed=0, input_seed=1, cont_ids=cont,
+               forced_prefill=forced[0], forced_turn=forced[1], preset="toy", torch_version=torch.__version__, **out_all)
+    torch.save(res, os.path.join(out_dir, "instruct_bf16_b1.pt"))
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-instruct" not in sys.argv:
+        main()
     with tempfile.TemporaryDirectory(dir=os.path.join(ROOT, "oracle")) as scratch:
-        multiround_case(os.path.join(ROOT, "tests", "golden"), scratch)
+        if "--only-instruct" not in sys.argv:
+            multiround_case(os.path.join(ROOT, "tests", "golden"), scratch)
+        instruct_case(os.path.join(ROOT, "tests", "golden"), scratch)

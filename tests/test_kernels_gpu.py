@@ -908,3 +908,63 @@ def test_im2col_patch_embed_matches_conv(L):
     torch.cuda.synchronize()
     ref_tok = torch.cat([cls.expand(B, 1, -1), pe], dim=1) + pos[None]
     assert torch.equal(tok.cpu(), ref_tok) and torch.equal(out.cpu(), ref_tok[:, 1:])
+
+
+# ---------------------------------------------------------------------------------------------- instruct predictor (new turn)
+@pytest.mark.parametrize("B,Tq,rate", [(1, 5, 0.5), (3, 70, 0.4), (2, 200, 0.9), (2, 1, 0.0), (3, 64, 0.0), (2, 129, 1.0)])
+def test_turn_decision_compact_advance(L, B, Tq, rate):
+    """cache_utils.py:165-241 via OracleCache.update(decision) per sample: slice to the true length, append the kept rows"""
+    nh, hd, Lr, SL = 3, 128, 4, 2
+    g = torch.Generator().manual_seed(7 * B + Tq)
+    logits = torch.randn(B, Tq, 2, generator=g).to(BF)
+    logits[:, :, 1] += (0.5 - rate) * 4
+    if Tq > 3:
+        logits[0, 2, 1] = logits[0, 2, 0]  # an exact tie is a drop (strict >)
+    want = logits[..., 0] > logits[..., 1]
+    want[:, -1:] = True  # dynamic_modeling_llama.py:2520
+    keep = torch.zeros(B * Tq, dtype=torch.uint8, device=DEV)
+    L.turn_decision(P(logits), None, P(keep), B, Tq, 1, ST())
+    assert torch.equal(keep.cpu().bool().view(B, Tq), want)
+    keep0 = torch.zeros(B * Tq, dtype=torch.uint8, device=DEV)
+    L.turn_decision(P(logits), None, P(keep0), B, Tq, 0, ST())
+    assert torch.equal(keep0.cpu().bool().view(B, Tq), logits[..., 0] > logits[..., 1])
+    forced = (torch.rand(B, Tq, generator=g) < 0.5)
+    keepf = torch.zeros(B * Tq, dtype=torch.uint8, device=DEV)
+    L.turn_decision(None, P(forced.to(torch.uint8)), P(keepf), B, Tq, 1, ST())
+    wf = forced.clone(); wf[:, -1] = True
+    assert torch.equal(keepf.cpu().bool().view(B, Tq), wf)
+    # arena with ragged cached lengths, new rows behind them
+    lens = torch.tensor([11, 0, 37][:B], dtype=torch.int32)
+    cap = int(lens.max()) + Tq + 5
+    K = rnd(B, nh, cap, hd, seed=3)
+    V = rnd(B, nh, cap, hd, seed=4)
+    Kd, Vd = K.to(DEV), V.to(DEV)
+    L.kv_compact_turn(P(Kd), P(Vd), P(lens), P(keep), Tq, B, nh, hd, cap, ST())
+    kv = torch.zeros(Lr, B, dtype=torch.int32, device=DEV) + lens.to(DEV)
+    pos = torch.full((B,), 100, dtype=torch.int32, device=DEV)
+    L.kv_advance_turn(P(kv), P(pos), P(keep), Lr, B, SL, Tq, ST())
+    torch.cuda.synchronize()
+    cnt = want.sum(1).to(torch.int32)
+    assert torch.equal(kv.cpu()[:SL], (lens + Tq).repeat(SL, 1)) and torch.equal(kv.cpu()[SL:], (lens + cnt).repeat(Lr - SL, 1))
+    assert pos.tolist() == [100 + Tq] * B
+    for b in range(B):
+        n0 = int(lens[b])
+        c = O.OracleCache()
+        c.k, c.v, c.true_len = [K[b: b + 1, :, :n0].clone()], [V[b: b + 1, :, :n0].clone()], [torch.tensor([n0])]
+        k_ref, v_ref = c.update(K[b: b + 1, :, n0: n0 + Tq], V[b: b + 1, :, n0: n0 + Tq], 0, want[b: b + 1])
+        n1 = n0 + int(cnt[b])
+        assert k_ref.shape[-2] == n1
+        assert torch.equal(Kd[b, :, :n1].cpu(), k_ref[0]) and torch.equal(Vd[b, :, :n1].cpu(), v_ref[0])
+        assert torch.equal(Kd[b, :, n0 + Tq:].cpu(), K[b, :, n0 + Tq:])  # nothing behind the new rows is touched
+
+
+def test_gather_rows_pos(L):
+    n, H = 57, 256
+    x = rnd(n, H, seed=9)
+    pos = torch.arange(n, dtype=torch.int32) * 3 + 1
+    idx = torch.tensor([0, 1, 2, 5, 9, 10, 30, 56, 56, 3], dtype=torch.int64)
+    out = torch.empty(len(idx), H, dtype=BF, device=DEV)
+    po = torch.empty(len(idx), dtype=torch.int32, device=DEV)
+    L.gather_rows_pos(P(x), P(pos), P(idx), P(out), P(po), len(idx), H, ST())
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), x[idx]) and torch.equal(po.cpu(), pos[idx])

@@ -353,6 +353,129 @@ def test_multiround_continuation_over_ragged_cache():
     assert torch.equal(cont.argmax(-1)[sure], g["cont_logits"].argmax(-1)[sure])
 
 
+def _instruct_model():
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    cfg["sparse_config"]["use_instruct_predictor"] = True
+    sd16 = {k: v.to(BF) for k, v in numpy_state_dict(cfg, seed=0).items()}
+    model = DynamicLlavaLlamaForCausalLM.from_state_dict(DynamicLlavaConfig(**cfg), sd16, device="cuda", dtype=BF)
+    return cfg, sd16, model
+
+
+@pytest.mark.parametrize("variant", ["natural", "forced"])
+def test_instruct_predictor_prefill_drop_and_new_turn(variant):
+    """use_instruct_predictor=True, pinned to the reference by tests/golden/instruct_bf16_b1.pt: instruction tokens dropped at the
+    sparse layer during the prefill (dynamic_modeling_llama.py:2261-2375) and per-token K/V persistence on a new user turn
+    (:2506-2521, cache_utils.py:165-241).  The predictor's own logits are compared with the reference's; its decisions are then
+    pinned to the reference's (natural: the reference's own decisions; forced: the fixture's +/-1 patterns) through a forward
+    hook, exactly as oracle/gen_golden.py does on the reference, so that a near-tie cannot fork the two runs."""
+    g = torch.load(os.path.join(GOLD, "instruct_bf16_b1.pt"), weights_only=False)
+    r = g[variant]
+    cfg, sd16, model = _instruct_model()
+    ids, pix = synthetic_inputs(cfg, 1, g["T"], seed=g["input_seed"], dtype=BF)
+    nat = [r["instruct_logits_prefill"], r["instruct_logits_turn"]]
+    if variant == "forced":
+        decs = [g["forced_prefill"], g["forced_turn"]]
+    else:
+        decs = [(x[0, :, 0] > x[0, :, 1]) for x in nat]
+    rec = {}
+    O.model_forward(sd16, cfg, ids, images=pix, record=rec, forced_instruct=decs[0])
+    keep = rec["keep_index"]
+    seen = []
+
+    def hook(mod, args, out):
+        seen.append(out.detach().float().cpu())
+        d = decs[len(seen) - 1].to(out.device)
+        z = torch.zeros_like(out)
+        z[..., 0] = torch.where(d.reshape(out.shape[:-1]), 1.0, -1.0).to(out.dtype)
+        return z
+    h = model.model.instruct_score_predictor.register_forward_hook(hook)
+    toks = r["tokens"]
+    lens_ref = r["true_len_hist"]
+    d_all = (lens_ref[1:, -1, 0] - lens_ref[:-1, -1, 0])
+    out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=keep)
+    got, lens = [out.logits[:, -1].cpu()], [torch.stack(list(out.past_key_values[1]), 0)]
+    past = out.past_key_values
+    for t in range(3):
+        out = model(torch.tensor([[toks[t]]]).cuda(), past_key_values=past, forced_text_decision=torch.tensor([bool(d_all[t])]))
+        past = out.past_key_values
+        got.append(out.logits[:, -1].cpu()); lens.append(torch.stack(list(past[1]), 0))
+    out = model(g["cont_ids"].cuda(), past_key_values=past)
+    past = out.past_key_values
+    cont = out.logits.cpu()
+    lens.append(torch.stack(list(past[1]), 0))
+    for t in range(3):
+        out = model(torch.tensor([[toks[3 + t]]]).cuda(), past_key_values=past, forced_text_decision=torch.tensor([bool(d_all[4 + t])]))
+        past = out.past_key_values
+        got.append(out.logits[:, -1].cpu()); lens.append(torch.stack(list(past[1]), 0))
+    h.remove()
+    assert len(seen) == 2
+    for mine, ref in zip(seen, nat):  # the predictor's own logits, before the hook pins the decision
+        assert mine.shape == ref.shape
+        assert (mine - ref.float()).abs().max() < 0.03 * max(1.0, ref.float().abs().max().item())
+        m_ref = (ref[..., 0] - ref[..., 1]).float()
+        clear = m_ref.abs() > 0.05
+        assert torch.equal((mine[..., 0] > mine[..., 1])[clear], (m_ref > 0)[clear])
+    assert torch.equal(torch.stack(lens, 0), lens_ref)
+    assert [k.shape[-2] for (k, v) in past[0]] == r["kv_shapes"].tolist()
+    scale = r["cont_logits"].abs().max().item()
+    assert cont.shape == r["cont_logits"].shape
+    assert (cont - r["cont_logits"]).abs().max() < 0.04 * scale
+    assert (torch.stack(got, 0) - r["step_logits"]).abs().max() < 0.04 * scale
+    top2 = r["cont_logits"].topk(2, dim=-1).values
+    sure = (top2[..., 0] - top2[..., 1]) > 0.08 * scale
+    assert torch.equal(cont.argmax(-1)[sure], r["cont_logits"].argmax(-1)[sure])
+
+
+def test_instruct_predictor_kv_rows_match_oracle():
+    """the rows persisted by a new turn are the oracle cache's rows (cache ++ kept new tokens), layer by layer"""
+    g = torch.load(os.path.join(GOLD, "instruct_bf16_b1.pt"), weights_only=False)
+    cfg, sd16, model = _instruct_model()
+    ids, pix = synthetic_inputs(cfg, 1, g["T"], seed=g["input_seed"], dtype=BF)
+    decs = [g["forced_prefill"], g["forced_turn"]]
+    rec = {}
+    lg, past_o = O.model_forward(sd16, cfg, ids, images=pix, record=rec, forced_instruct=decs[0])
+    _, past_o = O.model_forward(sd16, cfg, g["cont_ids"], past=past_o, forced_instruct=decs[1])
+    seen = []
+
+    def hook(mod, args, out):
+        d = decs[len(seen)].to(out.device)
+        seen.append(1)
+        z = torch.zeros_like(out)
+        z[..., 0] = torch.where(d.reshape(out.shape[:-1]), 1.0, -1.0).to(out.dtype)
+        return z
+    h = model.model.instruct_score_predictor.register_forward_hook(hook)
+    out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=rec["keep_index"])
+    out = model(g["cont_ids"].cuda(), past_key_values=out.past_key_values)
+    h.remove()
+    past = out.past_key_values
+    n_keep_turn = int(decs[1].clone().index_fill_(0, torch.tensor([len(decs[1]) - 1]), True).sum())
+    for l, (k_ref, v_ref) in enumerate(past_o[0]):
+        k, v = past[0][l]
+        assert k.shape == k_ref.shape, (l, k.shape, k_ref.shape)
+        tol = 0.05 * k_ref.float().abs().max().item()
+        assert (k.cpu().float() - k_ref.float()).abs().max() < tol and (v.cpu().float() - v_ref.float()).abs().max() < tol
+    SL = cfg["sparse_config"]["sparse_layer"]
+    assert past[0][SL][0].shape[-2] == past[0][0][0].shape[-2] - (16 - 8) - int((~decs[0]).sum()) - (5 - n_keep_turn)
+
+
+def test_instruct_predictor_batch_assert_and_generate():
+    """the reference asserts B == 1 in the prefill instruct branch (dynamic_modeling_llama.py:2270); generate() runs with it on"""
+    cfg, sd16, model = _instruct_model()
+    ids2, pix2 = synthetic_inputs(cfg, 2, 20, seed=1, dtype=BF)
+    with pytest.raises(AssertionError, match="batch size to 1"):
+        model(ids2.cuda(), images=pix2.cuda())
+    ids, pix = ids2[:1], pix2[:1]
+    out = model.generate(ids.cuda(), images=pix.cuda(), max_new_tokens=5, eos_token_id=None)
+    out2 = model.generate(ids.cuda(), images=pix.cuda(), max_new_tokens=5, eos_token_id=None)
+    assert out.shape == (1, 5) and torch.equal(out, out2)
+    o = model(ids.cuda(), images=pix.cuda())
+    assert int(o.logits[0, -1].argmax()) == int(out[0, 0])
+    n_hi = o.past_key_values[0][-1][0].shape[-2]
+    assert 35 - 8 - 13 <= n_hi <= 35 - 8
+
+
 @pytest.mark.timeout(300)
 def test_full_size_7b_config2_properties():
     """BASELINE config 2 at FULL size (LLaVA-1.5-7B dims, B=8, 32-id prompt + 336x336 image, keep 0.2, forced Bernoulli(0.5) output

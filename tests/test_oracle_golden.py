@@ -110,3 +110,27 @@ def test_multiround_continuation_matches_reference_bitexact(golden_dir):
     assert torch.equal(cont_lg, g["cont_logits"]) and torch.equal(logits, g["step_logits"])
     assert torch.equal(lens, g["true_len_hist"])
     assert [k.shape[-2] for (k, v) in past[0]] == g["kv_shapes"].tolist()
+
+
+@pytest.mark.parametrize("variant", ["natural", "forced"])
+def test_instruct_predictor_matches_reference_bitexact(golden_dir, variant):
+    """use_instruct_predictor=True: prefill-time instruction dropping (dynamic_modeling_llama.py:2261-2375) and
+    per-token persistence on a new user turn (:2506-2521, cache_utils.py:165-241)"""
+    g = torch.load(os.path.join(golden_dir, "instruct_bf16_b1.pt"), weights_only=False)
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    cfg["sparse_config"]["use_instruct_predictor"] = True
+    sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, seed=0).items()}
+    ids, pix = synthetic_inputs(cfg, 1, g["T"], seed=1, dtype=torch.bfloat16)
+    forced = variant == "forced"
+    rec = {}
+    logits, cont_lg, lens, toks, past = O.multiround_loop(sd, cfg, ids, pix, g["cont_ids"],
+                                                          forced_prefill=g["forced_prefill"] if forced else None,
+                                                          forced_turn=g["forced_turn"] if forced else None, record=rec)
+    r = g[variant]
+    assert toks == r["tokens"]
+    assert torch.equal(rec["instruct_logits_prefill"], r["instruct_logits_prefill"])
+    assert torch.equal(rec["instruct_logits_turn"], r["instruct_logits_turn"])
+    assert torch.equal(cont_lg, r["cont_logits"]) and torch.equal(logits, r["step_logits"])
+    assert torch.equal(lens, r["true_len_hist"])
+    assert [k.shape[-2] for (k, v) in past[0]] == r["kv_shapes"].tolist()
