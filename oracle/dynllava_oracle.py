@@ -241,9 +241,14 @@ def decoder_layer(sd, cfg, i, x, position_ids, cache, text_decision, cos, sin) -
 def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = None, inputs_embeds: Optional[Tensor] = None,
                   position_ids: Optional[Tensor] = None, past=None, indices: Optional[List[dict]] = None,
                   forced_keep_index: Optional[Tensor] = None, forced_text_decision: Optional[Tensor] = None,
-                  forced_instruct: Optional[Tensor] = None, record: Optional[dict] = None):
-    """DynamicLlamaModel.forward, eval + use_cache branches only (dynamic_modeling_llama.py:1656-2594), followed by
-    lm_head + .float() (:2709-2710).  Returns (logits fp32 [B, Lq', V], legacy past tuple).
+                  forced_instruct: Optional[Tensor] = None, record: Optional[dict] = None, use_cache: bool = True,
+                  state: Optional[dict] = None, forced_output_logits: Optional[dict] = None):
+    """DynamicLlamaModel.forward, eval branches only (dynamic_modeling_llama.py:1656-2594), followed by
+    lm_head + .float() (:2709-2710).  Returns (logits fp32 [B, Lq', V], legacy past tuple | None if not use_cache).
+
+    `use_cache=False` (:1703-1712, :2393-2504): no past is read or returned and the generated tokens between the sticky
+    `state["answer_indice"]` (the reference's `self.answer_indice`, :1644, :2402-2403) and the last token are thinned at the sparse
+    layer; `forced_output_logits` {n: [B,n,2]} replaces the output predictor's logits for an n-token span (what a forward hook does).
 
     `forced_keep_index` [B,k] / `forced_text_decision` [B,Lq] bool replace the predictors' own decisions
     (parity "under the same predictor masks"); `forced_instruct` bool [span] (prefill) / [Lq] (new turn)
@@ -251,7 +256,8 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
     sc = cfg["sparse_config"]
     if (input_ids is None) == (inputs_embeds is None):
         raise ValueError("You have to specify exactly one of input_ids or inputs_embeds")  # :1686-1695
-    cache = OracleCache.from_legacy(past)  # :1704-1712
+    cache = OracleCache.from_legacy(past if use_cache else None)  # :1703-1712 (use_cache=False: layers see no cache; a fresh one is
+    # bit-identical to `past_key_value=None` in :1056-1083 and is dropped at the end)
     x = F.embedding(input_ids, sd["model.embed_tokens.weight"]) if inputs_embeds is None else inputs_embeds
     B, seq = x.shape[:2]
     past_len0 = cache.length(0)
@@ -315,6 +321,24 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
                     record.update(text_logits=tl, text_decision_natural=text_decision)
                 if forced_text_decision is not None:
                     text_decision = forced_text_decision
+            elif have_idx and sc["use_output_text_predictor"] and not use_cache:  # :2393-2504 output stage without KV cache
+                if state.get("answer_indice") is None:  # :2402-2403 sticky across calls (post-image-drop coordinates)
+                    state["answer_indice"] = indices[0]["instruct"][1]
+                A = state["answer_indice"]
+                oh = x[:, A:-1, :]  # every generated token but the last; empty on the first two calls
+                tl = text_predictor(sd, oh).reshape(B, -1, 2)
+                if record is not None:
+                    record.update(text_logits=tl)
+                if forced_output_logits is not None and oh.shape[1] > 0:
+                    tl = forced_output_logits[oh.shape[1]].to(tl.dtype).reshape(tl.shape)
+                dec = tl[:, :, 0] > tl[:, :, 1]
+                n_keep = int(dec.sum(dim=1).max()) if dec.shape[1] else 0  # :2417 (torch: max of an empty-dim-1 sum is 0)
+                keep_o, _ = torch.sort(torch.argsort(tl[:, :, 0], dim=1, descending=True)[:, :n_keep], dim=1)  # :2420-2426
+                x = torch.cat([x[:, :A, :], oh.gather(1, keep_o[..., None].expand(B, n_keep, x.shape[2])), x[:, -1:, :]], dim=1)
+                position_ids = position_ids.expand(B, -1) if position_ids.shape[0] != B else position_ids
+                position_ids = torch.cat([position_ids[:, :A], position_ids[:, A:-1].gather(1, keep_o), position_ids[:, -1:]], dim=1)
+                if record is not None:
+                    record.update(output_keep_index=keep_o, position_ids=position_ids)
             elif past_len_i and x.shape[1] > 1 and sc["use_instruct_predictor"]:  # :2506-2521 new instruct turn
                 tl = text_predictor(sd, x, "model.instruct_score_predictor.").reshape(B, -1, 2)
                 text_decision = tl[:, :, 0] > tl[:, :, 1] if forced_instruct is None else forced_instruct.reshape(B, -1).clone()
@@ -328,7 +352,7 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
     if record is not None:
         record.update(final_hidden=x, text_decision=text_decision)
     logits = F.linear(x, sd["lm_head.weight"]).float()  # :2709-2710
-    return logits, cache.to_legacy()
+    return logits, (cache.to_legacy() if use_cache else None)  # :2570-2576
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -431,14 +455,16 @@ def prepare_multimodal(sd: StateDict, cfg: dict, input_ids: Tensor, pixels: Opti
 
 
 def model_forward(sd: StateDict, cfg: dict, input_ids: Tensor, *, images: Optional[Tensor] = None, past=None,
-                  forced_keep_index=None, forced_text_decision=None, forced_instruct=None, record=None):
+                  forced_keep_index=None, forced_text_decision=None, forced_instruct=None, record=None, use_cache=True, state=None,
+                  forced_output_logits=None):
     """DynamicLlavaLlamaForCausalLM.forward (language_model/dynamic_llava_llama.py:68-115)."""
     embeds, indices = prepare_multimodal(sd, cfg, input_ids, images)
     if embeds is None:
         return llama_forward(sd, cfg, input_ids=input_ids, past=past, forced_text_decision=forced_text_decision,
-                             forced_instruct=forced_instruct, record=record)
+                             forced_instruct=forced_instruct, record=record, use_cache=use_cache, state=state)
     return llama_forward(sd, cfg, inputs_embeds=embeds, past=past, indices=indices, forced_keep_index=forced_keep_index,
-                         forced_text_decision=forced_text_decision, forced_instruct=forced_instruct, record=record)
+                         forced_text_decision=forced_text_decision, forced_instruct=forced_instruct, record=record,
+                         use_cache=use_cache, state=state, forced_output_logits=forced_output_logits)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -544,3 +570,29 @@ def multiround_loop(sd, cfg, ids, pix, cont_ids, forced_prefill=None, forced_tur
         lg, past = model_forward(sd, cfg, nxt, past=past)
         logits.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
     return torch.stack(logits, 0), cont_lg, torch.stack(lens, 0), toks, past
+
+
+@torch.no_grad()
+def nocache_loop(sd, cfg, ids, pix, n_calls, forced_output_logits=None, forced_keep_index=None, teacher_tokens=None):
+    """llava/dynamic_eval/bench_test/dynamic_llava_long_text_time_with_no_cache.py:336-349: `model(total_ids, images, use_cache=False)`
+    with the id sequence growing by one token per call (greedy argmax, or `teacher_tokens` [B, n_calls], in place of the script's label
+    ids).  Returns per-call last-position logits, output lengths, the sparse layer's inputs and the final call's full logits."""
+    state = {"answer_indice": None}
+    total = ids.clone()
+    B = ids.shape[0]
+    last, lens, sl_in, text_logits, keep_o, full = [], [], [], [], [], None
+    SL = cfg["sparse_config"]["sparse_layer"]
+    for t in range(n_calls):
+        rec = {}
+        full, past = model_forward(sd, cfg, total, images=pix, use_cache=False, state=state, record=rec,
+                                   forced_output_logits=forced_output_logits, forced_keep_index=forced_keep_index)
+        assert past is None
+        last.append(full[:, -1].clone())
+        lens.append(full.shape[1])
+        sl_in.append(rec["layer_inputs"][SL])
+        text_logits.append(rec["text_logits"])
+        keep_o.append(rec["output_keep_index"])
+        nxt = full[:, -1].argmax(-1) if teacher_tokens is None else teacher_tokens[:, t]
+        total = torch.cat([total, nxt.reshape(B, 1)], dim=1)
+    return dict(tokens=total[:, ids.shape[1]:], last_logits=torch.stack(last, 0), seq_lens=lens, final_logits=full,
+                sparse_layer_inputs=sl_in, text_logits=text_logits, output_keep_index=keep_o, answer_indice=state["answer_indice"])

@@ -269,10 +269,75 @@ def instruct_case(out_dir, scratch):
     torch.save(res, os.path.join(out_dir, "instruct_bf16_b1.pt"))
 
 
+def nocache_forced_logits(n_max: int, B: int, seed: int = 13):
+    """Hook patterns for the no-KV-cache fixture: for every output-token count n (the hook is keyed by its input length, not by call
+    order) bf16-exact logits [B, n, 2] whose channel-0 scores are distinct within a sample (so `argsort` has no ties) and whose
+    `logit0 > logit1` counts differ between the samples (so `num_keep_node = max over the batch` is exercised)."""
+    rng = torch.Generator().manual_seed(seed)
+    out = {}
+    for n in range(1, n_max + 1):
+        z = torch.zeros(B, n, 2)
+        for b in range(B):
+            z[b, :, 0] = (torch.randperm(n, generator=rng).float() - (n - 1) / 2.0 + (0.75 if b % 2 else -0.75)) * 0.25
+        out[n] = z
+    return out
+
+
+@torch.no_grad()
+def nocache_case(out_dir, scratch):
+    """`use_cache=False` output sparsification (dynamic_modeling_llama.py:2393-2504): the loop of
+    llava/dynamic_eval/bench_test/dynamic_llava_long_text_time_with_no_cache.py:336-349 — the whole id sequence (prompt + tokens so
+    far) and the images are re-fed on every call, `model.model.answer_indice` stays at the first call's prompt end.  Greedy tokens take
+    the place of the script's label ids.  Variants: the predictor's own logits ("natural") and hook-injected ones ("forced")."""
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = numpy_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd, torch.bfloat16, scratch)
+    B, T, n_calls = 2, 12, 8
+    ids0, pix = synthetic_inputs(cfg, B, T, seed=1, dtype=torch.bfloat16)
+    forced = nocache_forced_logits(n_calls, B)
+    SL = cfg["sparse_config"]["sparse_layer"]
+    out_all = {}
+    for variant in ("natural", "forced"):
+        model.model.answer_indice = None
+        seen, sl_in = [], []
+
+        def hook(mod, args, out):
+            seen.append(out.detach().clone())
+            n = args[0].shape[1]
+            if variant == "natural" or n == 0:
+                return out
+            return forced[n].to(out.dtype).reshape(out.shape)
+        hs = [model.model.output_text_score_predictor.register_forward_hook(hook),
+              model.model.layers[SL].register_forward_pre_hook(
+                  lambda m, a, kw: sl_in.append((a[0] if a else kw["hidden_states"]).detach().clone()), with_kwargs=True)]
+        total = ids0.clone()
+        last_logits, lens, full = [], [], None
+        for t in range(n_calls):
+            out = model(total, images=pix, past_key_values=None, input_embeds_indices=None, use_cache=False)
+            assert out.past_key_values is None
+            last_logits.append(out.logits[:, -1].clone())
+            lens.append(out.logits.shape[1])
+            full = out.logits.clone()
+            total = torch.cat([total, out.logits[:, -1].argmax(-1).reshape(B, 1)], dim=1)
+        for h in hs:
+            h.remove()
+        out_all[variant] = dict(tokens=total[:, T:].clone(), last_logits=torch.stack(last_logits, 0), seq_lens=lens, final_logits=full,
+                                text_logits=seen, sparse_layer_inputs=sl_in, answer_indice=int(model.model.answer_indice))
+        print("nocache", variant, "tokens", total[:, T:].tolist(), "lens", lens, "answer_indice", model.model.answer_indice)
+    res = dict(name="toy_bf16_b2_nocache", dtype="torch.bfloat16", B=B, T=T, n_calls=n_calls, weight_seed=0, input_seed=1,
+               forced_logits=forced, preset="toy", torch_version=torch.__version__, **out_all)
+    torch.save(res, os.path.join(out_dir, "nocache_bf16_b2.pt"))
+
+
 if __name__ == "__main__":
-    if "--only-instruct" not in sys.argv:
+    only = [a for a in sys.argv[1:] if a.startswith("--only-")]
+    if not only:
         main()
     with tempfile.TemporaryDirectory(dir=os.path.join(ROOT, "oracle")) as scratch:
-        if "--only-instruct" not in sys.argv:
+        if not only:
             multiround_case(os.path.join(ROOT, "tests", "golden"), scratch)
-        instruct_case(os.path.join(ROOT, "tests", "golden"), scratch)
+        if not only or "--only-instruct" in only:
+            instruct_case(os.path.join(ROOT, "tests", "golden"), scratch)
+        if not only or "--only-nocache" in only:
+            nocache_case(os.path.join(ROOT, "tests", "golden"), scratch)

@@ -134,3 +134,27 @@ def test_instruct_predictor_matches_reference_bitexact(golden_dir, variant):
     assert torch.equal(cont_lg, r["cont_logits"]) and torch.equal(logits, r["step_logits"])
     assert torch.equal(lens, r["true_len_hist"])
     assert [k.shape[-2] for (k, v) in past[0]] == r["kv_shapes"].tolist()
+
+
+@pytest.mark.parametrize("variant", ["natural", "forced"])
+def test_nocache_output_sparsification_matches_reference_bitexact(golden_dir, variant):
+    """use_cache=False: the re-fed sequence loses generated tokens at the sparse layer by the output predictor's
+    top-`max count` scores (dynamic_modeling_llama.py:2393-2504), `answer_indice` sticky from the first call, the first call's
+    duplicated last token included (the `[answer_indice:-1]` slice is empty there)."""
+    g = torch.load(os.path.join(golden_dir, "nocache_bf16_b2.pt"), weights_only=False)
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, seed=0).items()}
+    ids, pix = synthetic_inputs(cfg, g["B"], g["T"], seed=1, dtype=torch.bfloat16)
+    r = O.nocache_loop(sd, cfg, ids, pix, g["n_calls"], forced_output_logits=g["forced_logits"] if variant == "forced" else None)
+    ref = g[variant]
+    assert r["answer_indice"] == ref["answer_indice"] and r["seq_lens"] == ref["seq_lens"]
+    assert ref["seq_lens"][0] == ref["answer_indice"] + 1  # the quirk: nothing to thin yet, the last token appears twice
+    assert torch.equal(r["tokens"], ref["tokens"])
+    assert torch.equal(r["last_logits"], ref["last_logits"]) and torch.equal(r["final_logits"], ref["final_logits"])
+    for a, b in zip(r["sparse_layer_inputs"], ref["sparse_layer_inputs"]):
+        assert torch.equal(a, b)
+    for a, b in zip(r["text_logits"], ref["text_logits"]):
+        assert torch.equal(a, b)
+    if variant == "forced":  # the hook patterns really thin the sequence, and by different per-sample counts
+        assert ref["seq_lens"][-1] < ref["answer_indice"] + g["n_calls"] - 1
