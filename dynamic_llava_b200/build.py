@@ -31,6 +31,7 @@ SOURCES = [
     "decode_fused.cu",
     "predictor_ops.cu",
     "sample.cu",
+    "nocache_select.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

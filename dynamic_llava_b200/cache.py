@@ -39,8 +39,11 @@ class RaggedKVArena:
         self.hi_exact = True
         self.floor_lo = self.floor_hi = 0  # host-known lower bounds of kv_len (set at prefill)
 
-    def reset(self):
-        for t in (self.k_lo, self.v_lo, self.k_hi, self.v_hi, self.kv_len, self.pos, self.step):
+    def reset(self, lengths_only: bool = False):
+        """lengths_only: a scratch arena (use_cache=False) is never served as a zero-padded legacy tuple, so the slabs may keep stale
+        rows beyond the lengths"""
+        for t in ((self.kv_len, self.pos, self.step) if lengths_only else
+                  (self.k_lo, self.v_lo, self.k_hi, self.v_hi, self.kv_len, self.pos, self.step)):
             t.zero_()
         self.keep.fill_(1)
         self.host_len_lo = self.host_ub_hi = 0

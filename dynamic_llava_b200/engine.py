@@ -68,8 +68,8 @@ class Session:
         self.indices = None
         self.n_steps_done = 0
 
-    def reset(self):
-        self.arena.reset()
+    def reset(self, lengths_only: bool = False):
+        self.arena.reset(lengths_only)
         self.finished.zero_()
         self.indices = None
         self.n_steps_done = 0
@@ -408,9 +408,11 @@ class Engine:
         return x
 
     @torch.no_grad()
-    def prefill(self, sess: Session, inputs_embeds, indices, forced_keep=None, all_logits=False, record=None):
+    def prefill(self, sess: Session, inputs_embeds, indices, forced_keep=None, all_logits=False, record=None, use_cache=True):
         """DynamicLlamaModel.forward, prefill branch (dynamic_modeling_llama.py:1656-2594) + lm_head (:2709).
-        inputs_embeds [B,P,H]; returns bf16 logits [B,V] (last position) or [B,P',V] if all_logits."""
+        inputs_embeds [B,P,H]; returns bf16 logits [B,V] (last position) or [B,P',V] if all_logits.
+        `use_cache=False` (:2393-2504): the sequence is prompt + tokens generated so far, re-fed whole; the generated
+        tokens between the sticky `model.model.answer_indice` and the last token are thinned at the sparse layer.  `sess` is scratch."""
         self._check_packed()
         c, sc = self.cfg, self.cfg.sparse_config
         m = self.model.model
@@ -479,6 +481,38 @@ class Engine:
                         d["answer"][1] -= drop
                     if record is not None:
                         record.update(instruct_logits=lg, instruct_keep_index=keep_i.view(1, -1), position_ids=pos.view(B, Lq))
+            elif (sc["use_text_predictor"] and sc["use_output_text_predictor"] and not use_cache and l == SL and have_idx):
+                # output stage without KV cache (:2393-2504; the instruct branch above precedes it in the reference's elif chain too)
+                if m.answer_indice is None:
+                    m.answer_indice = indices[0]["instruct"][1]  # :2402-2403, sticky; post-image-drop coordinates
+                A = int(m.answer_indice)
+                if A > Lq:
+                    raise ValueError(f"answer_indice {A} is beyond the sequence ({Lq}): reset model.model.answer_indice = None for a new prompt")
+                n_out = max(Lq - 1 - A, 0)  # the reference's [A:-1] slice; empty on the first two calls
+                n_keep, rank, keep_o = 0, None, None
+                if n_out > 0:
+                    if n_out > 8192:
+                        raise NotImplementedError("more than 8192 generated tokens in the no-cache mode (dl_output_rank limit)")
+                    lg = m.output_text_score_predictor(x.view(B, Lq, H)[:, A:Lq - 1, :]).contiguous()  # via __call__: hooks fire
+                    rank = torch.empty(B, n_out, device=self.device, dtype=torch.int32)
+                    cnt = torch.empty(B, device=self.device, dtype=torch.int32)
+                    self.L.output_rank(_p(lg), _p(rank), _p(cnt), B, n_out, _stream())
+                    n_keep = int(cnt.max())  # one host read for the new length, like the reference's slice by `num_keep_node` (:2417-2423)
+                    keep_o = torch.empty(B, n_keep, device=self.device, dtype=torch.int64)
+                    self.launches += 1
+                    if record is not None:
+                        record.update(text_logits=lg, output_keep_index=keep_o)
+                Ln = A + n_keep + 1  # left ++ kept ++ last: on the first call (Lq == A) the last token appears twice, as in the reference
+                rows = torch.empty(B, Ln, device=self.device, dtype=torch.int64)
+                self.L.output_keep_index(_p(rank), B, n_out, n_keep, A, Lq, _p(keep_o) if n_keep else None, _p(rows), _stream())
+                x_new = torch.empty(B * Ln, H, device=self.device, dtype=self.dtype)
+                pos_new = torch.empty(B * Ln, device=self.device, dtype=torch.int32)
+                self.L.gather_rows_pos(_p(x), _p(pos), _p(rows), _p(x_new), _p(pos_new), B * Ln, H, _stream())
+                self.launches += 2
+                x, pos, Lq = x_new, pos_new, Ln
+                cu = torch.arange(0, (B + 1) * Ln, Ln, device=self.device, dtype=torch.int32)
+                if record is not None:
+                    record.update(position_ids=pos.view(B, Lq))
             if record is not None:
                 record.setdefault("layer_inputs", []).append(x.view(B, Lq, H).clone())
             x = self._prefill_layer(l, x, pos, cu, sess, B, Lq)

@@ -186,15 +186,15 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                 vt._engine = ref
         return self._engine
 
-    def _session(self, B, cap_lo, cap_hi, max_new) -> Session:
-        key = (B, cap_lo, cap_hi, max_new)
+    def _session(self, B, cap_lo, cap_hi, max_new, scratch=False) -> Session:
+        key = (B, cap_lo, cap_hi, max_new, scratch)
         s = self._sessions.get(key)
         if s is None:
             self._sessions.clear()  # one live session per model: arenas are large
             s = Session(self.engine, B, cap_lo, cap_hi, max_new)
             self._sessions[key] = s
         else:
-            s.reset()
+            s.reset(lengths_only=scratch)
         return s
 
     def encode_images(self, images):
@@ -229,8 +229,8 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             raise ValueError("You have to specify either input_ids or inputs_embeds")
         if labels is not None or output_attentions or output_hidden_states:
             raise NotImplementedError("labels / output_attentions / output_hidden_states are outside the inference hot path")
-        if use_cache is False:
-            raise NotImplementedError("use_cache=False (no-KV-cache sparsification) is a SURVEY.md §8f 'next' row")
+        if use_cache is False and past_key_values is not None:
+            raise ValueError("use_cache=False re-feeds the whole sequence; it does not take past_key_values")
         sc = self.config.sparse_config
         eng = self.engine
         if inputs_embeds is None:
@@ -250,6 +250,14 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                 n_img = input_embeds_indices[0]["image"][1] - input_embeds_indices[0]["image"][0]
                 k_drop = n_img - int(n_img * sc["vision_keep_rate"])
             room = 64
+            if use_cache is False:
+                # no-KV-cache mode (bench_test/dynamic_llava_long_text_time_with_no_cache.py:336-349): the sequence grows by
+                # one id per call, so the scratch arena is sized in 256-token steps and reused; nothing is returned as a past
+                cap = -(-(P + room) // 256) * 256
+                sess = self._session(B, cap, cap, 0, scratch=True)
+                logits = eng.prefill(sess, inputs_embeds, input_embeds_indices, forced_keep=forced_keep_index, all_logits=True,
+                                     record=record, use_cache=False)
+                return CausalLMOutputWithPast(logits=logits.float(), past_key_values=None)
             sess = self._session(B, P + room, P - k_drop + room, 0)
             logits = eng.prefill(sess, inputs_embeds, input_embeds_indices, forced_keep=forced_keep_index, all_logits=True, record=record)
             past = LegacyPastView(sess.arena, sess)

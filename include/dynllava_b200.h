@@ -21,7 +21,8 @@
 extern "C" {
 #endif
 
-#define DL_B200_ABI_VERSION 3  /* 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points */
+#define DL_B200_ABI_VERSION 4  /* 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points;
+                                 * 4: no-KV-cache output sparsification (dl_output_rank / dl_output_keep_index) */
 
 int dl_version(void);
 const char* dl_last_error_string(void);
@@ -198,6 +199,17 @@ int dl_kv_advance_turn(int32_t* kv_len, int32_t* pos, const uint8_t* keep, int L
 /* out[i] = x[idx[i]] (rows of H bf16), pos_out[i] = pos[idx[i]]; idx int64 [n] on the device; pos/pos_out both NULL or both set. */
 int dl_gather_rows_pos(const void* x, const int32_t* pos, const int64_t* idx, void* out, int32_t* pos_out, int n, int H,
                        cudaStream_t stream);
+
+/* ---- no-KV-cache output sparsification (`use_cache=False`), DML:2393-2504 ---------------------------------------------------
+ * logits bf16 [B, n, 2] of the output text predictor over the n generated tokens between the sticky answer index and the last
+ * token.  rank int32 [B, n]: position of token i in the descending order of logit0 (ties: lower index first);
+ * count int32 [B] = #{logit0 > logit1}.  The caller reads count and takes n_keep = max_b count[b] (DML:2413-2417). n <= 8192. */
+int dl_output_rank(const void* logits, int32_t* rank, int32_t* count, int B, int n, cudaStream_t stream);
+/* keep_index int64 [B, n_keep] (NULL allowed) = ascending {i : rank[b,i] < n_keep} (DML:2420-2426); rows int64 [B, A+n_keep+1] =
+ * global source rows b*Lq + t of the thinned sequence [0, A) ++ A + keep_index ++ [Lq-1] (DML:2429-2455), A = answer_index.
+ * n may be 0 (rank NULL): the first call, where the reference's empty `[A:-1]` slice leaves left ++ last (DML:2405-2409). */
+int dl_output_keep_index(const int32_t* rank, int B, int n, int n_keep, int answer_index, int Lq, int64_t* keep_index,
+                         int64_t* rows, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -968,3 +968,48 @@ def test_gather_rows_pos(L):
     L.gather_rows_pos(P(x), P(pos), P(idx), P(out), P(po), len(idx), H, ST())
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), x[idx]) and torch.equal(po.cpu(), pos[idx])
+
+
+@pytest.mark.parametrize("B,n", [(1, 1), (2, 5), (3, 255), (2, 256), (2, 257), (3, 1000), (1, 4000)])
+def test_output_rank_and_keep_index(L, B, n):
+    """no-KV-cache output thinning (dynamic_modeling_llama.py:2411-2426): count = #{logit0 > logit1}, n_keep = max over the batch,
+    keep_index = sort(argsort(logit0, descending)[:, :n_keep]); ties resolved towards the lower index (a stable sort — torch's
+    CPU argsort is not stable, the reference leaves ties undefined).  Exact."""
+    g = torch.Generator().manual_seed(31 * B + n)
+    logits = torch.randn(B, n, 2, generator=g).to(BF)  # bf16 randn: plenty of exact ties once n > ~100
+    if n >= 5:
+        logits[0, 3, 0] = logits[0, 1, 0]
+        logits[0, 2, 1] = logits[0, 2, 0]  # logit0 == logit1 is a drop (strict >)
+    rank = torch.empty(B, n, dtype=torch.int32, device=DEV)
+    cnt = torch.empty(B, dtype=torch.int32, device=DEV)
+    L.output_rank(P(logits), P(rank), P(cnt), B, n, ST())
+    s0 = logits[..., 0].float()
+    order = torch.sort(s0, dim=1, descending=True, stable=True).indices
+    want_rank = torch.empty_like(order)
+    want_rank.scatter_(1, order, torch.arange(n).repeat(B, 1))
+    assert torch.equal(rank.cpu().long(), want_rank)
+    want_cnt = (logits[..., 0] > logits[..., 1]).sum(1)
+    assert torch.equal(cnt.cpu().long(), want_cnt)
+    A, tail = 7, 1
+    Lq = A + n + tail
+    for n_keep in sorted({int(want_cnt.max()), 0, n, max(n // 2, 0)}):
+        keep = torch.full((B, max(n_keep, 1)), -1, dtype=torch.int64, device=DEV)
+        rows = torch.full((B, A + n_keep + 1), -1, dtype=torch.int64, device=DEV)
+        L.output_keep_index(P(rank), B, n, n_keep, A, Lq, P(keep) if n_keep else None, P(rows), ST())
+        want_keep = torch.sort(order[:, :n_keep], dim=1).values
+        if n_keep:
+            assert torch.equal(keep.cpu(), want_keep)
+        base = (torch.arange(B) * Lq).view(B, 1)
+        want_rows = torch.cat([torch.arange(A).repeat(B, 1), want_keep + A, torch.full((B, 1), Lq - 1)], dim=1) + base
+        assert torch.equal(rows.cpu(), want_rows)
+
+
+def test_output_keep_index_first_call_duplicates_last_token(L):
+    """the reference's empty `[answer_indice:-1]` slice on the first call (Lq == A): left ++ last, i.e. the last token twice"""
+    B, A = 2, 19
+    rows = torch.full((B, A + 1), -1, dtype=torch.int64, device=DEV)
+    L.output_keep_index(None, B, 0, 0, A, A, None, P(rows), ST())
+    want = torch.cat([torch.arange(A), torch.tensor([A - 1])]).repeat(B, 1) + (torch.arange(B) * A).view(B, 1)
+    assert torch.equal(rows.cpu(), want)
+    with pytest.raises(RuntimeError):
+        L.output_keep_index(None, B, 4, 5, A, A + 5, None, P(rows), ST())  # n_keep > n

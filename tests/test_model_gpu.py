@@ -572,3 +572,100 @@ def test_generate_do_sample():
     assert torch.equal(x, model.generate(ids, do_sample=True, temperature=1.0, top_p=0.9, **kw).cpu())
     with pytest.raises(NotImplementedError):
         model.generate(ids, num_beams=3, **kw)
+
+
+def _nocache_setup():
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    g = torch.load(os.path.join(GOLD, "nocache_bf16_b2.pt"), weights_only=False)
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd32 = numpy_state_dict(cfg, seed=0)
+    sd16 = {k: v.to(BF) for k, v in sd32.items()}
+    model = DynamicLlavaLlamaForCausalLM.from_state_dict(DynamicLlavaConfig(**cfg), sd16, device="cuda", dtype=BF)
+    ids, pix = synthetic_inputs(cfg, g["B"], g["T"], seed=g["input_seed"], dtype=BF)
+    return g, cfg, sd32, sd16, model, ids, pix
+
+
+def test_nocache_output_sparsification_forced_logits():
+    """use_cache=False (dynamic_modeling_llama.py:2393-2504), pinned to the reference by tests/golden/nocache_bf16_b2.pt:
+    the loop of bench_test/dynamic_llava_long_text_time_with_no_cache.py:336-349 through OUR forward(), teacher-forced with the
+    reference's tokens.  The output predictor's logits are replaced by the fixture's patterns through a forward hook (what
+    oracle/gen_golden.py did on the reference) and the image mask is the oracle's, so the thinning is identical on both sides:
+    sequence lengths, kept indices and position ids are exact, the sparse layer's inputs and the logits are within the bf16 floor."""
+    g, cfg, sd32, sd16, model, ids, pix = _nocache_setup()
+    ref = g["forced"]
+    forced = g["forced_logits"]
+    rec0 = {}
+    O.model_forward(sd16, cfg, ids, images=pix, record=rec0)
+    keep = rec0["keep_index"]  # the image scores do not depend on later tokens (causal), so one mask serves every call
+    kw = dict(forced_output_logits=forced, forced_keep_index=keep, teacher_tokens=ref["tokens"])
+    o16 = O.nocache_loop(sd16, cfg, ids, pix, g["n_calls"], **kw)
+    o32 = O.nocache_loop(sd32, cfg, ids, pix.float(), g["n_calls"], **kw)
+    assert torch.equal(o16["last_logits"], ref["last_logits"])  # the oracle under its own mask == the reference run
+    floor = (o16["last_logits"] - o32["last_logits"]).abs().max().item()
+    scale = o32["last_logits"].abs().max().item()
+
+    def hook(mod, args, out):
+        n = args[0].shape[1]
+        return forced[n].to(out.device, out.dtype).reshape(out.shape)
+    h = model.model.output_text_score_predictor.register_forward_hook(hook)
+    assert model.model.answer_indice is None
+    SL = cfg["sparse_config"]["sparse_layer"]
+    total = ids.clone()
+    for t in range(g["n_calls"]):
+        rec = {}
+        out = model(total.cuda(), images=pix.cuda(), use_cache=False, forced_keep_index=keep, record=rec)
+        assert out.past_key_values is None
+        assert out.logits.shape[1] == ref["seq_lens"][t], (t, out.logits.shape, ref["seq_lens"])
+        assert torch.equal(rec["position_ids"].cpu().long(), _nocache_positions(o16, t, ref, keep, g))
+        if o16["output_keep_index"][t].shape[1]:
+            assert torch.equal(rec["output_keep_index"].cpu(), o16["output_keep_index"][t])
+        x_sl = rec["layer_inputs"][SL].float().cpu()
+        want = o32["sparse_layer_inputs"][t].float()
+        assert x_sl.shape == want.shape
+        assert (x_sl - want).abs().max() <= 2 * (o16["sparse_layer_inputs"][t].float() - want).abs().max() + 1e-2 * want.abs().max()
+        got = out.logits[:, -1].cpu()
+        assert (got - o32["last_logits"][t]).abs().max() <= 2 * floor + 1e-2 * scale, (t, (got - o32["last_logits"][t]).abs().max(), floor)
+        if t == g["n_calls"] - 1:
+            assert (out.logits.cpu() - o32["final_logits"]).abs().max() <= 2 * floor + 1e-2 * scale
+        total = torch.cat([total, ref["tokens"][:, t:t + 1]], dim=1)
+    h.remove()
+    assert model.model.answer_indice == ref["answer_indice"]
+    assert ref["seq_lens"][-1] < ref["answer_indice"] + g["n_calls"] - 1  # tokens really left the sequence
+    with pytest.raises(ValueError):
+        model(total.cuda(), images=pix.cuda(), use_cache=False, past_key_values=object())
+
+
+def _nocache_positions(o, t, ref, keep, g):
+    """position ids the thinned sequence must carry at call t: prompt positions after the image drop, the kept generated tokens'
+    original positions, the last token's (the first call repeats it)"""
+    B, T = g["B"], g["T"]
+    n_img, s0 = 16, 5
+    P = T - 1 + n_img + t
+    full = torch.arange(P).repeat(B, 1)
+    base = torch.cat([full[:, :s0], keep + s0, full[:, s0 + n_img:]], dim=1)
+    A = ref["answer_indice"]
+    ko = o["output_keep_index"][t]
+    return torch.cat([base[:, :A], base[:, A:-1].gather(1, ko), base[:, -1:]], dim=1)
+
+
+def test_nocache_natural_predictor_logits_and_sticky_answer_index():
+    """the output predictor's own logits over the generated span (the first call with a non-empty span sees inputs no earlier thinning
+    has touched) against the reference's, the sticky `answer_indice`, and the guard for a stale one"""
+    g, cfg, sd32, sd16, model, ids, pix = _nocache_setup()
+    ref = g["natural"]
+    total = torch.cat([ids, ref["tokens"][:, :2]], dim=1)
+    rec0 = {}
+    O.model_forward(sd16, cfg, ids, images=pix, record=rec0)
+    out0 = model(ids.cuda(), images=pix.cuda(), use_cache=False, forced_keep_index=rec0["keep_index"])
+    assert out0.logits.shape[1] == ref["answer_indice"] + 1 and model.model.answer_indice == ref["answer_indice"]
+    rec = {}
+    model(total.cuda(), images=pix.cuda(), use_cache=False, forced_keep_index=rec0["keep_index"], record=rec)
+    want = ref["text_logits"][2].float()
+    assert rec["text_logits"].shape == want.shape
+    assert (rec["text_logits"].float().cpu() - want).abs().max() < 0.03 * max(1.0, want.abs().max().item())
+    with pytest.raises(ValueError):
+        model(ids[:, :6].cuda(), images=pix.cuda(), use_cache=False)  # shorter than the sticky answer index: a new prompt needs a reset
+    model.model.answer_indice = None
+    out = model(ids[:, :8].cuda(), images=pix.cuda(), use_cache=False)
+    assert model.model.answer_indice == 8 - 1 + 8 and out.logits.shape[1] == model.model.answer_indice + 1
