@@ -116,6 +116,37 @@ class Conversation:
         raise ValueError(f"Invalid style: {self.sep_style}")
 
 
+# ------------------------------------------------------------------------------------------------------- stopping criteria
+class KeywordsStoppingCriteria:
+    """Behaviour of mm_utils.py:239-282 (a transformers `StoppingCriteria`; only the serving worker passes one).  A sequence is
+    finished when its tail equals one of the keywords' id sequences or when the decoded tail contains a keyword string; a batch
+    stops when every row is finished.  `generate(stopping_criteria=[...])` evaluates it on the host after every token, on the ids
+    generated so far (LLaVA hands `inputs_embeds` to HF, so `output_ids` never holds the prompt)."""
+
+    def __init__(self, keywords, tokenizer, input_ids):
+        self.keywords = list(keywords)
+        self.keyword_ids, self.max_keyword_len = [], 0
+        for kw in self.keywords:
+            ids = list(tokenizer(kw).input_ids)
+            if len(ids) > 1 and ids[0] == tokenizer.bos_token_id:
+                ids = ids[1:]
+            self.max_keyword_len = max(self.max_keyword_len, len(ids))
+            self.keyword_ids.append(torch.tensor(ids))
+        self.tokenizer = tokenizer
+        self.start_len = input_ids.shape[1]
+
+    def call_for_batch(self, output_ids, scores=None, **kwargs) -> bool:
+        offset = min(output_ids.shape[1] - self.start_len, self.max_keyword_len)
+        for kid in self.keyword_ids:
+            if torch.equal(output_ids[0, -kid.shape[0]:].cpu(), kid):
+                return True
+        text = self.tokenizer.batch_decode(output_ids[:, -offset:], skip_special_tokens=True)[0]
+        return any(kw in text for kw in self.keywords)
+
+    def __call__(self, output_ids, scores=None, **kwargs) -> bool:
+        return all(self.call_for_batch(output_ids[i].unsqueeze(0), scores) for i in range(output_ids.shape[0]))
+
+
 _VICUNA_SYSTEM = ("A chat between a curious user and an artificial intelligence assistant. "
                   "The assistant gives helpful, detailed, and polite answers to the user's questions.")
 

@@ -326,6 +326,10 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         forced_keep = kwargs.get("forced_keep_index")
         forced_dec = kwargs.get("forced_text_decisions")  # bool [n_steps >= max_new-1, B]
         use_graph = kwargs.get("use_cuda_graph", True)
+        # HF 4.37.2 greedy_search/sample: `if stopping_criteria(input_ids, scores): break` after every appended token, on the ids
+        # generated so far (LLaVA passes inputs_embeds, so HF's input_ids start empty).  Host callables -> one D2H read per token,
+        # paid only when a criterion is given (mm_utils.py:239-282 KeywordsStoppingCriteria; serve/model_worker.py is its one caller)
+        criteria = list(kwargs.get("stopping_criteria") or [])
         sc = self.config.sparse_config
         eng = self.engine
         dev = self.device
@@ -371,9 +375,9 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         pick(logits, eos_k if min_new <= 0 else None)
         eng.L.kv_advance(None, None, a.step.data_ptr(), None, 0, B, 0, 0, 0, torch.cuda.current_stream().cuda_stream)  # step += 1
         n_done = 1
-        graph = None
+        stopped = bool(criteria) and any(c(sess.tokens[:, :1].cpu(), None) for c in criteria)
         gkey = (use_dec, quirk, eos_k, pad, None if sess.forced is None else sess.forced.data_ptr(), sampling)
-        while n_done < max_new:
+        while n_done < max_new and not stopped:
             eos_now = eos_k if n_done >= min_new else None
             if use_graph and sess.graph is not None and sess.graph_key == gkey + (eos_now,):
                 sess.graph.replay()
@@ -400,6 +404,8 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                     continue
                 step()
             n_done += 1
+            if criteria:
+                stopped = any(c(sess.tokens[:, :n_done].cpu(), None) for c in criteria)
             if eos_k is not None and n_done % 16 == 0 and n_done < max_new:
                 if bool(sess.finished.all()):  # one host sync every 16 tokens
                     break

@@ -211,3 +211,36 @@ def test_host_prompt_and_image_prep():
     Cfg.image_aspect_ratio = "anyres"
     with pytest.raises(NotImplementedError):
         process_images([img], proc, Cfg())
+
+
+class _FakeTok:
+    """whitespace tokenizer: word -> id through a fixed table; bos = 1"""
+    bos_token_id = 1
+    table = {"</s>": 2, "###": 7, "Human": 8, "stop": 9, "now": 10}
+
+    def __call__(self, text):
+        class R:
+            pass
+        r = R()
+        r.input_ids = [1] + [self.table.get(w, 99) for w in text.split()]
+        return r
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        inv = {v: k for k, v in self.table.items()}
+        return [" ".join(inv.get(int(t), "x") for t in row) for row in ids]
+
+
+def test_keywords_stopping_criteria():
+    """mm_utils.py:239-282: id-suffix match first, decoded-tail substring match second, all rows must be finished"""
+    import torch
+    from llava.mm_utils import KeywordsStoppingCriteria
+    tok = _FakeTok()
+    prompt = torch.zeros(1, 0, dtype=torch.long)
+    c = KeywordsStoppingCriteria(["stop now", "###"], tok, prompt)
+    assert [k.tolist() for k in c.keyword_ids] == [[9, 10], [7]] and c.max_keyword_len == 2 and c.start_len == 0
+    assert not c(torch.tensor([[5, 9]]), None)
+    assert c(torch.tensor([[5, 9, 10]]), None)       # suffix ids == keyword ids
+    assert c(torch.tensor([[5, 6, 7]]), None)
+    assert not c(torch.tensor([[5, 6, 7], [5, 6, 6]]), None)   # every row has to be finished
+    assert c(torch.tensor([[5, 6, 7], [9, 10, 7]]), None)
+    assert not c(torch.tensor([[7, 5, 6]]), None)    # the keyword left the inspected tail

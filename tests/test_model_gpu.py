@@ -669,3 +669,21 @@ def test_nocache_natural_predictor_logits_and_sticky_answer_index():
     model.model.answer_indice = None
     out = model(ids[:, :8].cuda(), images=pix.cuda(), use_cache=False)
     assert model.model.answer_indice == 8 - 1 + 8 and out.logits.shape[1] == model.model.answer_indice + 1
+
+
+def test_generate_stopping_criteria():
+    """HF's `if stopping_criteria(input_ids, scores): break` after every appended token, on the generated ids only"""
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b2_forced", out_pred=True)
+    kw = dict(images=pix, max_new_tokens=10, eos_token_id=None, do_sample=False)
+    full = model.generate(ids, **kw).cpu()
+    seen = []
+
+    def crit(out_ids, scores, **_):
+        seen.append(tuple(out_ids.shape))
+        return out_ids.shape[1] >= 4
+    cut = model.generate(ids, stopping_criteria=[crit], **kw).cpu()
+    assert cut.shape == (g["B"], 4) and torch.equal(cut, full[:, :4])
+    assert seen == [(g["B"], n) for n in (1, 2, 3, 4)]
+    first = model.generate(ids, stopping_criteria=[lambda o, s: True], **kw).cpu()
+    assert first.shape == (g["B"], 1) and torch.equal(first, full[:, :1])
+    assert torch.equal(model.generate(ids, stopping_criteria=[lambda o, s: False], **kw).cpu(), full)
