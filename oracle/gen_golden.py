@@ -36,6 +36,7 @@ from llava.model.language_model.dynamic_llava_llama import (  # noqa: E402
 
 from dynamic_llava_b200.presets import SPARSE_DEFAULTS, preset  # noqa: E402
 from dynamic_llava_b200.synthetic import forced_text_decisions, numpy_state_dict, synthetic_inputs  # noqa: E402
+from oracle.cases import PREPARE_CASES, prepare_case_inputs  # noqa: E402
 
 
 class ShimCfg(DynamicLlavaConfig):
@@ -330,6 +331,31 @@ def nocache_case(out_dir, scratch):
     torch.save(res, os.path.join(out_dir, "nocache_bf16_b2.pt"))
 
 
+@torch.no_grad()
+def prepare_cases(out_dir, scratch):
+    """prepare_inputs_labels_for_multimodal alone (dynamic_llava_arch.py:169-601): spliced embeddings + the index dicts for the
+    edge cases the greedy fixtures do not reach."""
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = numpy_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd, torch.bfloat16, scratch)
+    res = {"preset": "toy", "weight_seed": 0, "torch_version": str(torch.__version__), "cases": {}}
+    for name in PREPARE_CASES:
+        ids, pix, kw = prepare_case_inputs(cfg, name)
+        model.config.tokenizer_model_max_length = kw.get("max_len")
+        model.config.tokenizer_padding_side = kw.get("padding_side", "right")
+        try:
+            (_, pos, mask, _, embeds, _), (indices,) = model.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, pix)
+        except IndexError as e:  # left padding + a row without a dict: the reference indexes input_embeds_indices[i] past its end (:556-566)
+            res["cases"][name] = {"raises": "IndexError"}
+            print("prepare", name, "-> reference raises IndexError:", e)
+            continue
+        assert pos is None and mask is None
+        res["cases"][name] = {"embeds": embeds.clone(), "indices": copy.deepcopy(indices)}
+        print("prepare", name, tuple(embeds.shape), indices)
+    torch.save(res, os.path.join(out_dir, "prepare_cases_bf16.pt"))
+
+
 if __name__ == "__main__":
     only = [a for a in sys.argv[1:] if a.startswith("--only-")]
     if not only:
@@ -339,5 +365,7 @@ if __name__ == "__main__":
             multiround_case(os.path.join(ROOT, "tests", "golden"), scratch)
         if not only or "--only-instruct" in only:
             instruct_case(os.path.join(ROOT, "tests", "golden"), scratch)
+        if not only or "--only-prepare" in only:
+            prepare_cases(os.path.join(ROOT, "tests", "golden"), scratch)
         if not only or "--only-nocache" in only:
             nocache_case(os.path.join(ROOT, "tests", "golden"), scratch)

@@ -158,3 +158,22 @@ def test_nocache_output_sparsification_matches_reference_bitexact(golden_dir, va
         assert torch.equal(a, b)
     if variant == "forced":  # the hook patterns really thin the sequence, and by different per-sample counts
         assert ref["seq_lens"][-1] < ref["answer_indice"] + g["n_calls"] - 1
+
+
+def test_prepare_multimodal_edge_cases_match_reference_bitexact(golden_dir):
+    """prepare_inputs_labels_for_multimodal alone (dynamic_llava_arch.py:169-601): spliced embeddings and index dicts for
+    `tokenizer_model_max_length` truncation, a placeholder right after BOS / as the last id, and a batch with a text-only row."""
+    from oracle.cases import PREPARE_CASES, prepare_case_inputs
+    g = torch.load(os.path.join(golden_dir, "prepare_cases_bf16.pt"), weights_only=False)
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, seed=0).items()}
+    assert set(g["cases"]) == set(PREPARE_CASES)
+    for name in PREPARE_CASES:
+        ids, pix, kw = prepare_case_inputs(cfg, name)
+        ref = g["cases"][name]
+        if "raises" in ref:  # left padding with a dict-less row: the reference itself fails (IndexError); nothing to pin
+            continue
+        embeds, indices = O.prepare_multimodal(sd, cfg, ids, pix, **kw)
+        assert indices == ref["indices"], (name, indices, ref["indices"])
+        assert torch.equal(embeds, ref["embeds"]), name
