@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the decode step eagerly (for ncu launch lists)")
     ap.add_argument("--cpu-new-tokens", type=int, default=4)
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' times the same oracle port (the reference's PyTorch op sequence: eager torch, cuBLAS, "
+                         "SDPA, torch.cat KV cache) on the GPU over the FULL workload — the like-for-like comparator of SURVEY.md §8d; the "
+                         "default (and what the driver runs) is the host-core baseline")
     return ap.parse_args()
 
 
@@ -362,10 +366,50 @@ def cpu_baseline(a, steps, warmup):
             "steps": steps}
 
 
+def gpu_comparator(a):
+    """"the same oracle is also timed on the B200 (reference PyTorch path, torch SDPA) as the like-for-like GPU comparator".
+    The oracle port with its tensors on cuda:0: eager torch ops, cuBLAS GEMMs, SDPA, a torch.cat-grown KV cache that is re-sliced,
+    zero-padded and re-stacked per layer per step for B > 1 (cache_utils.py:165-241) — what a user of the reference runs today.  Full
+    BASELINE config 2 workload (batch, prompt, forced Bernoulli decisions, new tokens), CUDA events, inputs resident on the device."""
+    from dynamic_llava_b200.presets import preset
+    from dynamic_llava_b200.synthetic import forced_text_decisions, synthetic_inputs, tiled_state_dict
+    from oracle import dynllava_oracle as O
+
+    dev = torch.device("cuda:0")
+    cfgd = preset(a.preset)
+    cfgd["sparse_config"]["vision_keep_rate"] = a.keep_rate
+    cfgd["sparse_config"]["use_output_text_predictor"] = a.out_keep >= 0
+    sd = {k: v.to(dev) for k, v in tiled_state_dict(cfgd, seed=0).items()}
+    ids, pix = synthetic_inputs(cfgd, a.batch, a.prompt_len, seed=1)
+    ids, pix = ids.to(dev), pix.to(dev)
+    fd = forced_text_decisions(a.new_tokens - 1, a.batch, keep_rate=a.out_keep, seed=3).to(dev) if a.out_keep >= 0 else None
+    ms = []
+    for it in range(a.warmup + max(a.steps, 1)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        O.greedy_loop(sd, cfgd, ids, pix, a.new_tokens, forced_text_decisions=fd)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= a.warmup:
+            ms.append(e0.elapsed_time(e1))
+    t = statistics.median(ms)
+    v = a.batch * a.new_tokens / (t / 1e3)
+    sample = (f"{a.preset} bf16 random-init (tiled), B={a.batch}, {a.prompt_len}-id prompt + 1 image, keep {a.keep_rate}, forced output decisions "
+              f"{a.out_keep}, {a.new_tokens} greedy tokens: the oracle port (reference op sequence, eager PyTorch) on {torch.cuda.get_device_name(0)}")
+    line = {"impl": "reference", "ref_device": "cuda", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2, full workload, reference PyTorch path on the GPU: " + sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if a.ref_device == "cuda":
+        return gpu_comparator(a)
     cb = cpu_baseline(a, steps=max(a.steps, 1), warmup=a.warmup)
     v = cb["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,

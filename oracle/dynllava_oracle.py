@@ -41,10 +41,10 @@ def rms_norm(x: Tensor, w: Tensor, eps: float) -> Tensor:
     return w * x32.to(dt)
 
 
-def rope_tables(head_dim: int, max_pos: int, theta: float, dtype) -> Tuple[Tensor, Tensor]:
+def rope_tables(head_dim: int, max_pos: int, theta: float, dtype, device=None) -> Tuple[Tensor, Tensor]:
     """dynamic_modeling_llama.py:152-184 — fp32 tables, half-split layout cat(freqs, freqs), cast on use."""
-    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2).float() / head_dim))
-    t = torch.arange(max_pos, dtype=inv_freq.dtype)
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=device).float() / head_dim))
+    t = torch.arange(max_pos, dtype=inv_freq.dtype, device=device)
     freqs = torch.outer(t, inv_freq)
     emb = torch.cat((freqs, freqs), dim=-1)
     return emb.cos().to(dtype), emb.sin().to(dtype)
@@ -107,7 +107,7 @@ class OracleCache:
         if len(self.k) <= layer:  # :139-149 first write (prefill)
             self.k.append(k_new)
             self.v.append(v_new)
-            self.true_len.append(decision.sum(dim=-1) if decision is not None else torch.tensor([N]).repeat(B))
+            self.true_len.append(decision.sum(dim=-1) if decision is not None else torch.tensor([N], device=k_new.device).repeat(B))
         elif decision is None:  # :242-250 plain append
             self.k[layer] = torch.cat([self.k[layer], k_new], dim=-2)
             self.v[layer] = torch.cat([self.v[layer], v_new], dim=-2)
@@ -217,10 +217,10 @@ def _attention(sd: StateDict, cfg: dict, i: int, x: Tensor, position_ids: Tensor
         # multi-token continuation over a cache (new user turn): the per-layer mask helper (:1805-1810, transformers
         # `_prepare_4d_causal_attention_mask_for_sdpa` with attention_mask=None, q_len > 1, kv > q) materialises a causal
         # 4-D additive mask offset by the cached length, and SDPA runs with is_causal=False (:1121)
-        m = torch.full((Lq, Lq), torch.finfo(q.dtype).min, dtype=q.dtype)
-        c = torch.arange(Lq)
+        m = torch.full((Lq, Lq), torch.finfo(q.dtype).min, dtype=q.dtype, device=q.device)
+        c = torch.arange(Lq, device=q.device)
         m.masked_fill_(c < (c + 1).view(Lq, 1), 0)
-        m = torch.cat([torch.zeros(Lq, past_i, dtype=q.dtype), m], dim=-1)[None, None].expand(B, 1, Lq, past_i + Lq)
+        m = torch.cat([torch.zeros(Lq, past_i, dtype=q.dtype, device=q.device), m], dim=-1)[None, None].expand(B, 1, Lq, past_i + Lq)
         o = F.scaled_dot_product_attention(q, k_all, v_all, attn_mask=m, dropout_p=0.0, is_causal=False)
     else:
         o = F.scaled_dot_product_attention(q, k_all, v_all, attn_mask=None, dropout_p=0.0, is_causal=Lq > 1)  # :1114-1122
@@ -262,10 +262,10 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
     B, seq = x.shape[:2]
     past_len0 = cache.length(0)
     if position_ids is None:  # :1714-1722
-        position_ids = torch.arange(past_len0, seq + past_len0, dtype=torch.long).unsqueeze(0)
+        position_ids = torch.arange(past_len0, seq + past_len0, dtype=torch.long, device=x.device).unsqueeze(0)
     init_n = seq
     nh = cfg["num_attention_heads"]
-    cos, sin = rope_tables(cfg["hidden_size"] // nh, cfg["max_position_embeddings"], cfg["rope_theta"], x.dtype)
+    cos, sin = rope_tables(cfg["hidden_size"] // nh, cfg["max_position_embeddings"], cfg["rope_theta"], x.dtype, x.device)
     have_idx = indices is not None and B == len(indices)
     text_decision = None
     SL = sc["sparse_layer"]
@@ -279,14 +279,14 @@ def llama_forward(sd: StateDict, cfg: dict, *, input_ids: Optional[Tensor] = Non
             imgs = [x[b, indices[b]["image"][0]: indices[b]["image"][1], :] for b in range(B)]  # :1832-1842
             mx = max(t.shape[0] for t in imgs)
             img_x = torch.stack([torch.cat([t, t.new_zeros(mx - t.shape[0], t.shape[1])], dim=0) for t in imgs])
-            policy = torch.ones(B, n_img, 1, dtype=x.dtype)
+            policy = torch.ones(B, n_img, 1, dtype=x.dtype, device=x.device)
             logits = vision_predictor(sd, img_x, policy, sc["nhead"]).reshape(B, -1, 2)
             n_keep = int(n_img * sc["vision_keep_rate"])  # :1899-1901
             keep = topk_keep_index(logits, n_keep) if forced_keep_index is None else forced_keep_index
             gathered = x[:, s0:e0, :].gather(1, keep[..., None].expand(B, n_keep, x.shape[2]))  # :1935-1942
             x = torch.cat([x[:, :s0, :], gathered, x[:, e0:, :]], dim=1)  # :1944-1951
             position_ids = torch.cat(
-                [torch.arange(0, s0).repeat(B, 1), keep + s0, torch.arange(e0, init_n).repeat(B, 1)], dim=1
+                [torch.arange(0, s0, device=x.device).repeat(B, 1), keep + s0, torch.arange(e0, init_n, device=x.device).repeat(B, 1)], dim=1
             ).to(torch.long)  # :1962-1983
             drop = n_img - n_keep  # :1985-1994 (mutates the caller's dicts, as the reference does)
             for d in indices:
@@ -425,7 +425,7 @@ def prepare_multimodal(sd: StateDict, cfg: dict, input_ids: Tensor, pixels: Opti
         sys_e, ins_e, ans_e = text[:s], text[s: ans - 1], text[ans - 1: T - 1]  # :368-396
         e = torch.cat([sys_e, img, ins_e, ans_e])  # :398-405
         embeds.append(e)
-        user = torch.tensor(USER_IDS)
+        user = torch.tensor(USER_IDS, device=ids.device)
         m = [j for j in range(len(ins_ids) - len(user) + 1) if torch.equal(ins_ids[j: j + len(user)], user)]  # :418-454
         last = m[-1] if len(m) else 0
         i0 = sys_e.shape[0]
