@@ -521,6 +521,64 @@ def test_full_size_7b_config2_properties():
 
 
 @pytest.mark.timeout(400)
+def test_full_size_7b_configs3_and_5_properties():
+    """BASELINE configs 3 and 5 per GPU at FULL size (LLaVA-1.5-7B dims), through size-independent properties.
+      * config 3 (ragged-KV stress: 8 samples per GPU, 256 new tokens, per-sample forced keep rates linspace(0.1, 0.9, 8)): layers >=
+        sparse_layer hold exactly P' + (#kept decisions of that sample) keys — the lengths diverge by up to ~200 keys — layers below
+        hold P + n - 1; CUDA-graph replay == eager loop token for token;
+      * config 5 (keep-rate sweep {0.1, 0.2, 0.5, 1.0}, batch 16, run-time mutation of the live sparse_config like the reference's
+        bench script): k = int(576 * rate), P' = 607 - 576 + k, lengths per layer class, the keep index is ascending, in range and
+        duplicate-free per sample, and at rate 1.0 it is the identity."""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    from dynamic_llava_b200.presets import preset
+    from dynamic_llava_b200.synthetic import device_state_dict, forced_text_decisions, synthetic_inputs
+    cfgd = preset("llava-1.5-7b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = True
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device="cuda")
+    model.get_vision_tower().load_model()
+    model.load_state_dict(device_state_dict(cfgd, seed=0, device="cuda"), strict=True)
+    SL, L = cfgd["sparse_config"]["sparse_layer"], cfgd["num_hidden_layers"]
+    # ---- config 3 ----
+    B, T, n_new = 8, 32, 256
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    ids, pix = ids.cuda(), pix.cuda()
+    rates = torch.linspace(0.1, 0.9, B).tolist()
+    fd = forced_text_decisions(n_new - 1, B, keep_rate=rates, seed=3)
+    kw = dict(images=pix, max_new_tokens=n_new, do_sample=False, eos_token_id=None, forced_text_decisions=fd)
+    out1 = model.generate(ids, **kw).cpu()
+    lens = next(iter(model._sessions.values())).arena.kv_len.cpu().long()
+    kept = fd.sum(0).long()
+    assert int(kept.max() - kept.min()) > 100  # the stress is real: per-sample lengths far apart
+    assert lens[:SL].eq(607 + n_new - 1).all()
+    for l in range(SL, L):
+        assert lens[l].tolist() == (146 + kept).tolist(), l
+    assert torch.equal(out1, model.generate(ids, use_cuda_graph=False, **kw).cpu())
+    # ---- config 5 ----
+    B = 16
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=2)
+    ids, pix = ids.cuda(), pix.cuda()
+    model.config.sparse_config["use_output_text_predictor"] = False
+    for rate in (0.1, 0.2, 0.5, 1.0):
+        model.config.sparse_config["vision_keep_rate"] = rate
+        k = int(576 * rate)
+        rec = {}
+        out = model(ids, images=pix, record=rec)
+        assert out.logits.shape[1] == 607 - 576 + k
+        keep = rec["keep_index"].cpu()
+        assert keep.shape == (B, k) and int(keep.min()) >= 0 and int(keep.max()) < 576
+        assert bool((keep[:, 1:] > keep[:, :-1]).all())
+        if k == 576:
+            assert torch.equal(keep, torch.arange(576).repeat(B, 1))
+        pos = rec["position_ids"].cpu().long()
+        want = torch.cat([torch.arange(5).repeat(B, 1), keep + 5, torch.arange(5 + 576, 607).repeat(B, 1)], dim=1)
+        assert torch.equal(pos, want)
+        lens = torch.stack(list(out.past_key_values[1]), 0)
+        assert lens[:SL].eq(607).all() and lens[SL:].eq(607 - 576 + k).all()
+    del model
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.timeout(400)
 def test_full_size_13b_config4_prefill_properties():
     """BASELINE config 4 per GPU (LLaVA-1.5-13B dims, B=4, full embedded length P = 2048 -> P' = 1587 at keep 0.2, prefill + 2 tokens),
     through the same size-independent properties: KV bookkeeping per layer class, determinism, half-batch bookkeeping (the long-sequence
