@@ -355,8 +355,12 @@ class Engine:
             indices.append({"system": [0, i0], "image": [i0, i1], "instruct": [i1, i2], "answer": [i2, i2],
                             "last_instruct": [i1 + last, i2]})
         P = max((T - 1 + n_img) if p >= 0 else T for p in img_pos)
-        if padding_side != "right":
-            raise NotImplementedError("left padding (tokenizer_padding_side='left') is not on the supported path")
+        if padding_side != "right" and any(p < 0 for p in img_pos) and any(p >= 0 for p in img_pos):
+            # rows are rectangular ids with one placeholder each, so padding only ever appears next to a row WITHOUT an image; with
+            # `tokenizer_padding_side="left"` the reference itself fails there (IndexError on its per-row dict list,
+            # dynamic_llava_arch.py:556-566; tests/golden/prepare_cases_bf16.pt "text_only_row_left").  Every other left-padded flow
+            # pads nothing and is served as is.
+            raise NotImplementedError("left padding next to a row without an image (the reference raises IndexError here)")
         H = self.cfg.hidden_size
         out = torch.empty(B, P, H, device=self.device, dtype=self.dtype)
         ids_dev = input_ids.to(self.device, torch.int64).contiguous()

@@ -774,7 +774,12 @@ def test_prepare_multimodal_edge_cases_against_reference_golden():
             is_img[b, d["image"][0]: d["image"][1]] = True
         assert torch.equal(e[~is_img], r[~is_img]), name
         assert (e[is_img] - r[is_img]).abs().max() <= 0.03 * max(1.0, r[is_img].abs().max().item()), name
+    # left padding pads nothing when every row carries an image: same result as right padding
+    ids, pix, _ = prepare_case_inputs(cfg, "base")
     model.config.tokenizer_model_max_length = None
+    model.config.tokenizer_padding_side = "left"
+    (_, _, _, _, e_left, _), (i_left,) = model.prepare_inputs_labels_for_multimodal(ids.cuda(), None, None, None, None, pix.cuda())
+    assert i_left == g["cases"]["base"]["indices"] and e_left.shape == g["cases"]["base"]["embeds"].shape
     model.config.tokenizer_padding_side = "right"
     # a batch whose rows do not all carry an image runs dense (no dict for the text-only row -> the sparsifier's guard fails, like the
     # reference's `hidden_states.shape[0] == len(input_embeds_indices)`)
