@@ -55,8 +55,8 @@ def parse():
 def kernel_rooflines(dev):
     """untimed extras: live rooflines of the two other kernels the north star names — K2 (prefill attention, tensor pipe) on the
     L=2048 stress shape and on this workload's own shapes, K1 (select + gather/compact, HBM) on the 13B B=32 shape and on this
-    workload's 19 MB.  CUDA events over back-to-back launches (K2: 50 after 10 warm-ups, K1: 20 after 3); K1 rotates buffers beyond
-    the 126 MB L2."""
+    workload's 19 MB.  CUDA events around one CUDA-graph replay of back-to-back launches (K2: 50 after 10 warm-ups, K1: 20 after 3); K1
+    rotates buffers beyond the 126 MB L2."""
     import ctypes
     import math
     from dynamic_llava_b200._lib import lib
@@ -68,13 +68,25 @@ def kernel_rooflines(dev):
     hbm_peak = float(pk.get("hbm_gbs", 6650.0))
 
     def timeit(fn, n_rot=1, iters=20, warm=3):
+        """ms per launch inside ONE CUDA-graph replay of `iters` launches (CUDA events around the replay).  Eager ctypes launches cost
+        ~13 us of host time each (more with tensor-map encoding), which hid every kernel shorter than that
+        (profiles/r1_k1_warp_select_experiment.md); a replay has no host in the loop."""
         for i in range(warm):
             fn(i % n_rot)
         torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for i in range(iters):
+                    fn(i % n_rot)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()  # warm replay
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters):
-            fn(i % n_rot)
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
