@@ -786,3 +786,78 @@ def test_prepare_multimodal_edge_cases_against_reference_golden():
     ids, pix, _ = prepare_case_inputs(cfg, "text_only_row")
     out = model(ids.cuda(), images=pix.cuda())
     assert out.logits.shape[1] == 27
+
+
+def _nocache_properties(model, cfgd, B, T, n_calls, tol_rel):
+    """size-independent properties of the no-KV-cache mode (any model size):
+      (1) a predictor that keeps every generated token (hooked logits +1/-1) thins nothing, so from the second call on the logits are
+          BIT-IDENTICAL to the dense re-feed (`use_output_text_predictor=False`): same kernels, same shapes, the gather is a copy; the
+          first call alone differs by the reference's duplicated last token (one more position);
+      (2) the dense re-feed's last-position logits agree with the cached path (prefill + q_len=1 decode steps without drops, teacher-forced
+          with the same tokens) up to bf16 noise — two different kernel paths (prefill attention over the re-fed sequence vs ragged decode
+          attention over the KV arena) computing the same function."""
+    sc = model.config.sparse_config
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    ids, pix = ids.cuda(), pix.cuda()
+    g = torch.Generator().manual_seed(5)
+    teacher = torch.randint(3, cfgd["vocab_size"], (B, n_calls), generator=g).cuda()
+    n_img = (cfgd["vision"]["image_size"] // cfgd["vision"]["patch_size"]) ** 2
+    Pp = T - 1 + int(n_img * sc["vision_keep_rate"])
+
+    def refeed(flag, hook=None):
+        sc["use_output_text_predictor"] = flag
+        model.model.answer_indice = None
+        h = model.model.output_text_score_predictor.register_forward_hook(hook) if hook is not None else None
+        total, outs = ids.clone(), []
+        for t in range(n_calls):
+            outs.append(model(total, images=pix, use_cache=False).logits)
+            total = torch.cat([total, teacher[:, t:t + 1]], dim=1)
+        if h is not None:
+            h.remove()
+        return outs
+
+    def keep_all(mod, args, out):
+        z = torch.zeros_like(out)
+        z[..., 0], z[..., 1] = 1.0, -1.0
+        return z
+    dense = refeed(False)
+    kept = refeed(True, keep_all)
+    assert kept[0].shape[1] == Pp + 1 and dense[0].shape[1] == Pp  # the first call's duplicated last token
+    for t in range(1, n_calls):
+        assert kept[t].shape[1] == Pp + t
+        assert torch.equal(kept[t], dense[t]), t
+    # (2) cached path, no drops
+    sc["use_output_text_predictor"] = False
+    out = model(ids, images=pix)
+    cached = [out.logits[:, -1]]
+    for t in range(n_calls - 1):
+        out = model(teacher[:, t:t + 1], past_key_values=out.past_key_values)
+        cached.append(out.logits[:, -1])
+    worst = 0.0
+    for t in range(n_calls):
+        a, b = dense[t][:, -1].float(), cached[t].float()
+        scale = max(b.abs().max().item(), 1e-6)
+        worst = max(worst, (a - b).abs().max().item() / scale)
+    assert worst <= tol_rel, worst
+    sc["use_output_text_predictor"] = True
+    model.model.answer_indice = None
+
+
+def test_nocache_properties_toy():
+    g, cfg, sd32, sd16, model, ids, pix = _nocache_setup()
+    _nocache_properties(model, cfg, B=3, T=12, n_calls=6, tol_rel=3e-2)
+
+
+@pytest.mark.timeout(300)
+def test_nocache_properties_full_size_7b():
+    """the same properties at LLaVA-1.5-7B dims (batch 4, the reference script's default; 32-id prompt + 336x336 image, keep 0.2)"""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    from dynamic_llava_b200.synthetic import device_state_dict
+    cfgd = preset("llava-1.5-7b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = True
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device="cuda")
+    model.get_vision_tower().load_model()
+    model.load_state_dict(device_state_dict(cfgd, seed=0, device="cuda"), strict=True)
+    _nocache_properties(model, cfgd, B=4, T=32, n_calls=5, tol_rel=5e-2)
+    del model
+    torch.cuda.empty_cache()
