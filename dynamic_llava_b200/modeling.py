@@ -302,6 +302,9 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         kwargs.pop("input_embeds_indices", None)
         if "inputs_embeds" in kwargs:
             raise NotImplementedError("`inputs_embeds` is not supported")
+        if kwargs.get("use_cache", True) is False:
+            raise NotImplementedError("generate(use_cache=False): drive the no-KV-cache mode through forward(..., use_cache=False) like the "
+                                      "reference's bench_test/dynamic_llava_long_text_time_with_no_cache.py; generate() always decodes over the cache")
         if kwargs.get("num_beams", 1) not in (1, None):
             raise NotImplementedError("beam search is a SURVEY.md §8f 'next' row; num_beams must be 1")
         sampling = None  # (temperature, top_k, top_p): HF 4.37.2 `sample` (model_vqa_loader.py:169-172: do_sample = temperature > 0)

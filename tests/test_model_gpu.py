@@ -630,6 +630,8 @@ def test_generate_do_sample():
     assert torch.equal(x, model.generate(ids, do_sample=True, temperature=1.0, top_p=0.9, **kw).cpu())
     with pytest.raises(NotImplementedError):
         model.generate(ids, num_beams=3, **kw)
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, use_cache=False, **kw)
 
 
 def _nocache_setup():
