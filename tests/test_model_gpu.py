@@ -863,3 +863,54 @@ def test_nocache_properties_full_size_7b():
     _nocache_properties(model, cfgd, B=4, T=32, n_calls=5, tol_rel=5e-2)
     del model
     torch.cuda.empty_cache()
+
+
+@pytest.mark.timeout(600)
+def test_full_size_7b_config1_against_cpu_oracle():
+    """BASELINE config 1, the parity anchor, at FULL size against the CPU oracle itself: LLaVA-1.5-7B dims (random init, tiled pool),
+    one 336x336 image, 32-id prompt, keep 0.2, 16 greedy tokens, `use_output_text_predictor=False` (the reference's image-bench setting).
+    The oracle runs on the host cores in bf16 (~10 s) and in fp32 (~15 s, the noise floor); the B200 path runs under the oracle's own
+    image mask, teacher-forced with the oracle's tokens.  Bars: logits within 2*floor + 1e-2*max|logit| of the fp32 oracle at every step
+    (floor = the oracle's own bf16-vs-fp32 distance, ~3 % of the logit scale at 32 layers); KV lengths exact (607+15 / 146+15); the token
+    the B200 path would pick is, in the fp32 oracle's eyes, within that same bound of the oracle's best token (random-init margins are
+    far below the bf16 floor, so exact token equality is reported, not required)."""
+    import psutil
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    from dynamic_llava_b200.synthetic import tiled_state_dict
+    if psutil.virtual_memory().available < 50e9:
+        pytest.skip("needs ~45 GB of host RAM for the bf16 + fp32 oracle weights")
+    torch.set_num_threads(os.cpu_count() or 8)
+    cfgd = preset("llava-1.5-7b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = False
+    sd16 = tiled_state_dict(cfgd, seed=0)
+    B, T, n_new = 1, 32, 16
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    o16 = O.greedy_loop(sd16, cfgd, ids, pix, n_new)
+    keep = o16["keep_index"]
+    model = DynamicLlavaLlamaForCausalLM.from_state_dict(DynamicLlavaConfig(**cfgd), sd16, device="cuda", dtype=BF)
+    got, past = _gpu_teacher_forced(model, {"n_new": n_new, "tokens": o16["tokens"]}, ids, pix, keep, None)
+    lens = torch.stack(list(past[1]), 0)
+    free_gen = model.generate(ids.cuda(), images=pix.cuda(), max_new_tokens=n_new, do_sample=False, eos_token_id=None,
+                              forced_keep_index=keep).cpu()
+    del model
+    torch.cuda.empty_cache()
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    del sd16
+    o32 = O.greedy_loop(sd32, cfgd, ids, pix.float(), n_new, forced_keep_index=keep, teacher_tokens=o16["tokens"])
+    del sd32
+    floor = (o16["logits"] - o32["logits"]).abs().max().item()
+    scale = o32["logits"].abs().max().item()
+    bound = 2 * floor + 1e-2 * scale
+    err = (got - o32["logits"]).abs().max().item()
+    assert err <= bound, (err, floor, scale)
+    SL, L = cfgd["sparse_config"]["sparse_layer"], cfgd["num_hidden_layers"]
+    assert torch.equal(lens, o16["true_len"])
+    assert lens[:SL].eq(607 + n_new - 1).all() and lens[SL:].eq(146 + n_new - 1).all()
+    pick = got.argmax(-1)  # [n_new, B]
+    ref_at_pick = o32["logits"].gather(-1, pick.unsqueeze(-1)).squeeze(-1)
+    assert bool((o32["logits"].max(-1).values - ref_at_pick <= bound).all())
+    agree = (pick == o32["logits"].argmax(-1)).float().mean().item()
+    first = int(free_gen[0, 0])
+    assert first == int(pick[0, 0])  # generate() and the hand-rolled forward loop start from the same prefill
+    print(f"config 1 @7B: max|gpu - oracle_fp32| = {err:.4f} (floor {floor:.4f}, scale {scale:.3f}); teacher-forced argmax agreement {agree:.2f}; "
+          f"free-running tokens {free_gen[0].tolist()} vs oracle {o16['tokens'][0].tolist()}")
