@@ -520,31 +520,42 @@ def greedy_loop(sd: StateDict, cfg: dict, input_ids: Tensor, images: Tensor, n_n
 
 
 @torch.no_grad()
-def hf_greedy_generate(sd: StateDict, cfg: dict, input_ids: Tensor, images: Tensor, max_new_tokens: int,
-                       eos_token_id: Optional[int] = 2, pad_token_id: int = 0, **forced):
-    """transformers-4.37.2 `GenerationMixin.generate` greedy search as entered from
-    language_model/dynamic_llava_llama.py:146-152 (restated from documented behaviour; PARITY
-    UNPINNED — HF 4.37.2 is not in this container).  Rows that already produced EOS emit `pad_token_id`; stops when
-    every row has finished; returns ONLY the new tokens (the prompt was passed as embeddings)."""
-    B = input_ids.shape[0]
-    past, ids = None, input_ids
-    unfinished = torch.ones(B, dtype=torch.long)
-    out = []
-    ftd_all = forced.get("forced_text_decisions")
+def hf_greedy_search(step_fn, batch: int, max_new_tokens: int, eos_token_id: Optional[int] = 2, pad_token_id: int = 0) -> Tensor:
+    """The bookkeeping of transformers' greedy search (4.37.2 `GenerationMixin.greedy_search`, restated from documented behaviour,
+    SURVEY.md App. C): `step_fn(t, prev)` returns the last-position logits [B, V] of call t (prev = the tokens fed back, None at t = 0).
+    Rows that already produced EOS emit `pad_token_id`; the loop stops when every row has finished; only new tokens are returned.
+    4.37.2 is not installable here; tests/test_oracle_golden.py pins this loop token for token against the installed transformers'
+    own `generate` (greedy, inputs_embeds entry, ragged EOS) on a stand-in Llama."""
+    unfinished = torch.ones(batch, dtype=torch.long)
+    out, prev = [], None
     for t in range(max_new_tokens):
-        ftd = ftd_all[t - 1].reshape(-1, 1) if (t > 0 and ftd_all is not None) else None
-        logits, past = model_forward(sd, cfg, ids, images=images if t == 0 else None, past=past,
-                                     forced_keep_index=forced.get("forced_keep_index") if t == 0 else None,
-                                     forced_text_decision=ftd)
-        nxt = torch.argmax(logits[:, -1, :], dim=-1)
+        nxt = torch.argmax(step_fn(t, prev), dim=-1).cpu()
         if eos_token_id is not None:
             nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
             unfinished = unfinished * (nxt != eos_token_id).long()
         out.append(nxt)
-        ids = nxt.reshape(-1, 1)
+        prev = nxt
         if eos_token_id is not None and int(unfinished.max()) == 0:
             break
     return torch.stack(out, 1)
+
+
+def hf_greedy_generate(sd: StateDict, cfg: dict, input_ids: Tensor, images: Tensor, max_new_tokens: int,
+                       eos_token_id: Optional[int] = 2, pad_token_id: int = 0, **forced):
+    """`generate` as entered from language_model/dynamic_llava_llama.py:146-152: the greedy-search bookkeeping above around the
+    reference forward (prompt as embeddings + images at t = 0, then one id per call over the returned past).  PARITY UNPINNED against
+    transformers 4.37.2 itself (not in this container); the loop semantics are pinned to the installed transformers (see above)."""
+    ftd_all = forced.get("forced_text_decisions")
+    state = {"past": None}
+
+    def step(t, prev):
+        ids = input_ids if t == 0 else prev.reshape(-1, 1).to(input_ids.device)
+        ftd = ftd_all[t - 1].reshape(-1, 1) if (t > 0 and ftd_all is not None) else None
+        logits, state["past"] = model_forward(sd, cfg, ids, images=images if t == 0 else None, past=state["past"],
+                                              forced_keep_index=forced.get("forced_keep_index") if t == 0 else None,
+                                              forced_text_decision=ftd)
+        return logits[:, -1, :]
+    return hf_greedy_search(step, input_ids.shape[0], max_new_tokens, eos_token_id, pad_token_id)
 
 
 @torch.no_grad()

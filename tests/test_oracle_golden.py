@@ -177,3 +177,65 @@ def test_prepare_multimodal_edge_cases_match_reference_bitexact(golden_dir):
         embeds, indices = O.prepare_multimodal(sd, cfg, ids, pix, **kw)
         assert indices == ref["indices"], (name, indices, ref["indices"])
         assert torch.equal(embeds, ref["embeds"]), name
+
+
+def test_hf_greedy_search_bookkeeping_matches_installed_transformers():
+    """`O.hf_greedy_search` (EOS -> pad for finished rows, stop when all rows are finished, new tokens only) against the INSTALLED
+    transformers' own `generate` (greedy, entered with `inputs_embeds` like dynamic_llava_llama.py:146-152) on a stand-in Llama with a
+    ragged EOS pattern.  transformers 4.37.2 (the reference's pin) is not installable here; this pins the restated loop to a real HF
+    implementation of the same search."""
+    transformers = pytest.importorskip("transformers")
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(0)
+    hcfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=2,
+                       vocab_size=48, max_position_embeddings=128, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+    model = LlamaForCausalLM(hcfg).eval()
+    B, P, n_new = 4, 7, 12
+    embeds = torch.randn(B, P, 64) * 0.5
+
+    def run_hf(eos, rows=slice(None)):
+        e = embeds[rows]
+        kw = dict(inputs_embeds=e, attention_mask=torch.ones(e.shape[0], P, dtype=torch.long), do_sample=False, max_new_tokens=n_new,
+                  pad_token_id=0, num_beams=1)
+        # "no EOS": an id outside the vocabulary can never fire
+        return model.generate(eos_token_id=hcfg.vocab_size + 5 if eos is None else eos, **kw)
+
+    def run_mine(eos, rows=slice(None)):
+        st = {"past": None}
+        e = embeds[rows]
+
+        def step(t, prev):
+            with torch.no_grad():
+                if t == 0:
+                    o = model(inputs_embeds=e, use_cache=True)
+                else:
+                    o = model(input_ids=prev.reshape(-1, 1), past_key_values=st["past"], use_cache=True)
+            st["past"] = o.past_key_values
+            return o.logits[:, -1, :]
+        return O.hf_greedy_search(step, e.shape[0], n_new, eos, 0)
+    with torch.no_grad():
+        free = run_hf(None)
+    assert free.shape == (B, n_new)
+    assert torch.equal(run_mine(None), free)
+    # an EOS id that rows reach at different steps (and one row possibly never): the token row 0 emits at step 3
+    eos = int(free[0, 3])
+    with torch.no_grad():
+        hf = run_hf(eos)
+    mine = run_mine(eos)
+    assert hf.shape[1] <= n_new
+    assert torch.equal(mine, hf), (mine, hf)
+    hit = (free == eos).any(1)
+    assert bool(hit[0])
+    first = int((free[0] == eos).float().argmax())
+    assert (hf[0, first + 1:] == 0).all()  # finished rows are padded
+    # every row finishes, at different steps: the search stops early and the output is shorter than max_new_tokens
+    counts = torch.stack([(free[1:] == tok).any(1).all() for tok in range(hcfg.vocab_size)])
+    common = [tok for tok in range(hcfg.vocab_size) if bool(counts[tok])]
+    assert common, "seeded stand-in lost its common token; pick another seed"
+    eos2 = common[0]
+    steps = [(free[r] == eos2).float().argmax().item() for r in range(1, B)]
+    with torch.no_grad():
+        hf2 = run_hf(eos2, slice(1, None))
+    mine2 = run_mine(eos2, slice(1, None))
+    assert torch.equal(mine2, hf2), (mine2, hf2)
+    assert hf2.shape[1] == int(max(steps)) + 1 < n_new and len(set(steps)) > 1
