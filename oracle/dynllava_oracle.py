@@ -520,6 +520,24 @@ def greedy_loop(sd: StateDict, cfg: dict, input_ids: Tensor, images: Tensor, n_n
 
 
 @torch.no_grad()
+def hf_warped_probs(logits: Tensor, temperature: float, top_k: int, top_p: float) -> Tensor:
+    """The distribution HF's `sample` draws from: TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper -> softmax
+    (transformers logits_process.py, min_tokens_to_keep = 1; top_k = 0 / top_p = 1 switch a warper off), on the fp32 logits the
+    reference hands to generate() (dynamic_modeling_llama.py:2710, model_vqa_loader.py:169-172).  Restated; pinned against the installed
+    transformers' warper classes in tests/test_oracle_golden.py (4.37.2 itself is not installable here)."""
+    scores = logits.float() / temperature
+    if top_k > 0:
+        kth = torch.topk(scores, min(top_k, scores.shape[-1]))[0][..., -1, None]
+        scores = scores.masked_fill(scores < kth, float("-inf"))
+    if top_p < 1.0:
+        srt, idx = torch.sort(scores, descending=False)
+        cum = srt.softmax(dim=-1).cumsum(dim=-1)
+        rem = cum <= (1 - top_p)
+        rem[..., -1:] = False
+        scores = scores.masked_fill(rem.scatter(1, idx, rem), float("-inf"))
+    return scores.softmax(dim=-1)
+
+
 def hf_greedy_search(step_fn, batch: int, max_new_tokens: int, eos_token_id: Optional[int] = 2, pad_token_id: int = 0) -> Tensor:
     """The bookkeeping of transformers' greedy search (4.37.2 `GenerationMixin.greedy_search`, restated from documented behaviour,
     SURVEY.md App. C): `step_fn(t, prev)` returns the last-position logits [B, V] of call t (prev = the tokens fed back, None at t = 0).

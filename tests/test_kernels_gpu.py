@@ -267,20 +267,7 @@ def test_select_compact_forced_and_ties(L):
 
 
 # ---------------------------------------------------------------------------------------------- sampling
-def _hf_warped_probs(logits, temperature, top_k, top_p):
-    """torch restatement of transformers 4.37.2 TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper -> softmax
-    (logits_process.py; min_tokens_to_keep = 1), on the fp32 logits the reference hands to generate()."""
-    scores = logits.float() / temperature
-    if top_k > 0:
-        kth = torch.topk(scores, min(top_k, scores.shape[-1]))[0][..., -1, None]
-        scores = scores.masked_fill(scores < kth, float("-inf"))
-    if top_p < 1.0:
-        srt, idx = torch.sort(scores, descending=False)
-        cum = srt.softmax(dim=-1).cumsum(dim=-1)
-        rem = cum <= (1 - top_p)
-        rem[..., -1:] = False
-        scores = scores.masked_fill(rem.scatter(1, idx, rem), float("-inf"))
-    return scores.softmax(dim=-1)
+_hf_warped_probs = O.hf_warped_probs  # pinned on CPU against the installed transformers' warpers (tests/test_oracle_golden.py)
 
 
 def _sample(L, logits, step, seed, temperature, top_k, top_p, want_probs=True, eos=-1):

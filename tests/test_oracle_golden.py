@@ -239,3 +239,24 @@ def test_hf_greedy_search_bookkeeping_matches_installed_transformers():
     mine2 = run_mine(eos2, slice(1, None))
     assert torch.equal(mine2, hf2), (mine2, hf2)
     assert hf2.shape[1] == int(max(steps)) + 1 < n_new and len(set(steps)) > 1
+
+
+@pytest.mark.parametrize("temperature,top_k,top_p", [(0.2, 50, 1.0), (1.0, 0, 0.9), (0.7, 50, 0.7), (1.3, 5, 0.5), (0.2, 0, 1.0), (1.0, 1, 0.3)])
+def test_hf_warped_probs_match_installed_transformers(temperature, top_k, top_p):
+    """`O.hf_warped_probs` (what tests/test_kernels_gpu.py checks dl_sample_next against) == the installed transformers' own
+    TemperatureLogitsWarper -> TopKLogitsWarper -> TopPLogitsWarper chain followed by softmax, bit for bit, ties included."""
+    pytest.importorskip("transformers")
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+    g = torch.Generator().manual_seed(17)
+    logits = (torch.randn(5, 512, generator=g) * 3).to(torch.bfloat16).float()  # bf16-valued logits: exact ties occur
+    ids = torch.zeros(5, 1, dtype=torch.long)
+    s = logits.clone()
+    if temperature != 1.0:
+        s = TemperatureLogitsWarper(temperature)(ids, s)
+    if top_k > 0:
+        s = TopKLogitsWarper(top_k=top_k, min_tokens_to_keep=1)(ids, s)
+    if top_p < 1.0:
+        s = TopPLogitsWarper(top_p=top_p, min_tokens_to_keep=1)(ids, s)
+    want = s.softmax(dim=-1)
+    got = O.hf_warped_probs(logits, temperature, top_k, top_p)
+    assert torch.equal(got, want), (got - want).abs().max()
