@@ -152,7 +152,9 @@ _VICUNA_SYSTEM = ("A chat between a curious user and an artificial intelligence 
 
 conv_vicuna_v1 = Conversation(system=_VICUNA_SYSTEM, roles=("USER", "ASSISTANT"), messages=[], offset=0,
                               sep_style=SeparatorStyle.TWO, sep=" ", sep2="</s>", version="v1")
-conv_llava_v1 = Conversation(system=_VICUNA_SYSTEM, roles=("USER", "ASSISTANT"), messages=[], offset=0,
+_LLAVA_V1_SYSTEM = ("A chat between a curious human and an artificial intelligence assistant. "
+                    "The assistant gives helpful, detailed, and polite answers to the human's questions.")  # conversation.py:289-299 ("human", not "user")
+conv_llava_v1 = Conversation(system=_LLAVA_V1_SYSTEM, roles=("USER", "ASSISTANT"), messages=[], offset=0,
                              sep_style=SeparatorStyle.TWO, sep=" ", sep2="</s>", version="v1")
 conv_llava_plain = Conversation(system="", roles=("", ""), messages=[], offset=0, sep_style=SeparatorStyle.PLAIN, sep="\n", sep2=None)
 

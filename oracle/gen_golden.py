@@ -356,6 +356,53 @@ def prepare_cases(out_dir, scratch):
     torch.save(res, os.path.join(out_dir, "prepare_cases_bf16.pt"))
 
 
+def host_prep_cases(out_dir):
+    """The reference's own host-side helpers (llava/conversation.py, llava/mm_utils.py) run on the shared fixtures of oracle/cases.py:
+    prompt strings, tokenizer_image_token ids (BOS and no-BOS tokenizers), KeywordsStoppingCriteria decisions, get_model_name_from_path,
+    expand2square + process_images ("pad" and default) pixel tensors."""
+    from llava.conversation import conv_templates
+    from llava.mm_utils import KeywordsStoppingCriteria, expand2square, get_model_name_from_path, process_images, tokenizer_image_token
+    from oracle import cases as C
+    import llava
+    assert llava.__file__.startswith("/root/reference"), llava.__file__
+    res = {"prompts": [], "token_ids": {}, "stopping": [], "model_names": {}, "torch_version": str(torch.__version__)}
+    for name, turns in C.HOST_PROMPTS:
+        conv = conv_templates[name].copy()
+        for q, a in turns:
+            conv.append_message(conv.roles[0], q)
+            conv.append_message(conv.roles[1], a)
+        try:
+            res["prompts"].append(conv.get_prompt())
+        except TypeError:  # "plain" with an answer: sep2 is None in the reference's template (conversation.py:106)
+            res["prompts"].append({"raises": "TypeError"})
+    for no_bos in (False, True):
+        tok = C.ToyTokenizer(no_bos)
+        for p in C.TOKENIZE_PROMPTS + [q for q in res["prompts"] if isinstance(q, str)]:
+            res["token_ids"][(no_bos, p)] = tokenizer_image_token(p, tok, -200)
+    tok = C.ToyTokenizer()
+    crit = KeywordsStoppingCriteria(C.STOP_KEYWORDS, tok, torch.zeros(1, 0, dtype=torch.long))
+    res["stopping_meta"] = {"keyword_ids": [k.tolist() for k in crit.keyword_ids], "max_keyword_len": crit.max_keyword_len, "start_len": crit.start_len}
+    for seq in C.STOP_SEQUENCES:
+        res["stopping"].append(bool(crit(torch.tensor(seq), None)))
+    for p in C.MODEL_PATHS:
+        try:
+            res["model_names"][p] = get_model_name_from_path(p)
+        except IndexError:  # a bare "checkpoint-N" has no parent component (mm_utils.py:233-234)
+            res["model_names"][p] = {"raises": "IndexError"}
+    proc = CLIPImageProcessor(size={"shortest_edge": 56}, crop_size={"height": 56, "width": 56})
+    img = C.host_image()
+    sq = expand2square(img, (10, 20, 30))
+    res["square"] = torch.from_numpy(__import__("numpy").array(sq))
+
+    class Cfg:
+        image_aspect_ratio = "pad"
+    res["pixels_pad"] = process_images([img, img.transpose(2)], proc, Cfg())  # 2 = ROTATE_90: a tall image too
+    Cfg.image_aspect_ratio = None
+    res["pixels_default"] = process_images([img], proc, Cfg())
+    torch.save(res, os.path.join(out_dir, "host_prep_cases.pt"))
+    print("host prep:", len(res["prompts"]), "prompts,", len(res["token_ids"]), "tokenisations,", res["stopping"], res["model_names"])
+
+
 if __name__ == "__main__":
     only = [a for a in sys.argv[1:] if a.startswith("--only-")]
     if not only:
@@ -365,6 +412,8 @@ if __name__ == "__main__":
             multiround_case(os.path.join(ROOT, "tests", "golden"), scratch)
         if not only or "--only-instruct" in only:
             instruct_case(os.path.join(ROOT, "tests", "golden"), scratch)
+        if not only or "--only-hostprep" in only:
+            host_prep_cases(os.path.join(ROOT, "tests", "golden"))
         if not only or "--only-prepare" in only:
             prepare_cases(os.path.join(ROOT, "tests", "golden"), scratch)
         if not only or "--only-nocache" in only:

@@ -244,3 +244,51 @@ def test_keywords_stopping_criteria():
     assert not c(torch.tensor([[5, 6, 7], [5, 6, 6]]), None)   # every row has to be finished
     assert c(torch.tensor([[5, 6, 7], [9, 10, 7]]), None)
     assert not c(torch.tensor([[7, 5, 6]]), None)    # the keyword left the inspected tail
+
+
+def test_host_prep_matches_reference_golden():
+    """conv templates, tokenizer_image_token, KeywordsStoppingCriteria, get_model_name_from_path, expand2square and process_images against
+    the outputs of the REFERENCE's own llava/conversation.py and llava/mm_utils.py on the shared fixtures (oracle/cases.py ->
+    oracle/gen_golden.py --only-hostprep -> tests/golden/host_prep_cases.pt), error cases included."""
+    import numpy as np
+    import torch
+    from transformers import CLIPImageProcessor
+    from llava.conversation import conv_templates
+    from llava.mm_utils import KeywordsStoppingCriteria, expand2square, get_model_name_from_path, process_images, tokenizer_image_token
+    from oracle import cases as C
+    import llava
+    assert not llava.__file__.startswith("/root/reference")  # the shim package of THIS repo is under test
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "host_prep_cases.pt"), weights_only=False)
+    for (name, turns), want in zip(C.HOST_PROMPTS, g["prompts"]):
+        conv = conv_templates[name].copy()
+        for q, a in turns:
+            conv.append_message(conv.roles[0], q)
+            conv.append_message(conv.roles[1], a)
+        if isinstance(want, dict):
+            with pytest.raises(TypeError):
+                conv.get_prompt()
+        else:
+            assert conv.get_prompt() == want, name
+    assert len(g["token_ids"]) == 20
+    for (no_bos, prompt), want in g["token_ids"].items():
+        assert tokenizer_image_token(prompt, C.ToyTokenizer(no_bos), -200) == want, (no_bos, prompt)
+    crit = KeywordsStoppingCriteria(C.STOP_KEYWORDS, C.ToyTokenizer(), torch.zeros(1, 0, dtype=torch.long))
+    meta = g["stopping_meta"]
+    assert [k.tolist() for k in crit.keyword_ids] == meta["keyword_ids"] and crit.max_keyword_len == meta["max_keyword_len"]
+    assert crit.start_len == meta["start_len"]
+    assert [bool(crit(torch.tensor(s), None)) for s in C.STOP_SEQUENCES] == g["stopping"]
+    for p, want in g["model_names"].items():
+        if isinstance(want, dict):
+            with pytest.raises(IndexError):
+                get_model_name_from_path(p)
+        else:
+            assert get_model_name_from_path(p) == want
+    img = C.host_image()
+    assert torch.equal(torch.from_numpy(np.array(expand2square(img, (10, 20, 30)))), g["square"])
+    proc = CLIPImageProcessor(size={"shortest_edge": 56}, crop_size={"height": 56, "width": 56})
+
+    class Cfg:
+        image_aspect_ratio = "pad"
+    assert torch.equal(process_images([img, img.transpose(2)], proc, Cfg()), g["pixels_pad"])
+    Cfg.image_aspect_ratio = None
+    assert torch.equal(process_images([img], proc, Cfg()), g["pixels_default"])
