@@ -340,6 +340,10 @@ def prepare_cases(out_dir, scratch):
     sd = numpy_state_dict(cfg, seed=0)
     model = build_reference(cfg, sd, torch.bfloat16, scratch)
     res = {"preset": "toy", "weight_seed": 0, "torch_version": str(torch.__version__), "cases": {}}
+    # the checkpoint contract: every key and shape of the reference model's state_dict (toy dims, both text predictors off/on as built)
+    res["state_dict_shapes"] = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    import llava.constants as RC
+    res["constants"] = {k: getattr(RC, k) for k in dir(RC) if k.isupper()}
     for name in PREPARE_CASES:
         ids, pix, kw = prepare_case_inputs(cfg, name)
         model.config.tokenizer_model_max_length = kw.get("max_len")

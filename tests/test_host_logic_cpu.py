@@ -292,3 +292,21 @@ def test_host_prep_matches_reference_golden():
     assert torch.equal(process_images([img, img.transpose(2)], proc, Cfg()), g["pixels_pad"])
     Cfg.image_aspect_ratio = None
     assert torch.equal(process_images([img], proc, Cfg()), g["pixels_default"])
+
+
+def test_state_dict_contract_and_constants_match_reference_golden():
+    """every state_dict key AND shape of the reference model (toy dims; built by oracle/gen_golden.py from the unmodified reference
+    classes) against this package's model, plus llava.constants — the checkpoint / import contract of SURVEY §8b"""
+    import torch
+    import llava.constants as C
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "prepare_cases_bf16.pt"), weights_only=False)
+    cfg = DynamicLlavaConfig.from_preset("toy")
+    cfg.sparse_config["use_output_text_predictor"] = True
+    m = DynamicLlavaLlamaForCausalLM(cfg, device="cpu")
+    m.get_vision_tower().load_model()
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = {k: v for k, v in g["state_dict_shapes"].items() if "rotary_emb" not in k and not k.endswith("position_ids")}
+    assert set(mine) == set(ref), (sorted(set(mine) ^ set(ref))[:8])
+    assert mine == ref
+    for k, v in g["constants"].items():
+        assert getattr(C, k) == v, k
