@@ -72,6 +72,15 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
             "mm_projector_type", "mm_hidden_size", "mm_vision_select_layer", "mm_vision_select_feature", "mm_patch_merge_type",
             "mm_use_im_start_end", "mm_use_im_patch_token", "image_aspect_ratio", "tokenizer_padding_side",
             "tokenizer_model_max_length", "sparse_config", "max_sequence_length")
+    if cfg_json.get("rope_theta") is None and isinstance(cfg_json.get("rope_parameters"), dict):
+        # config.json written under transformers 5.x: rope_theta moved into rope_parameters (4.37.2 wrote it at the top level)
+        rp = cfg_json["rope_parameters"]
+        if rp.get("rope_type", "default") != "default":
+            raise NotImplementedError(f"rope scaling ({rp.get('rope_type')}) is not used by LLaVA-1.5 and not supported")
+        if rp.get("rope_theta") is not None:
+            cfg_json["rope_theta"] = rp["rope_theta"]
+    if cfg_json.get("rope_scaling") not in (None, {}):
+        raise NotImplementedError("rope scaling is not used by LLaVA-1.5 and not supported")
     cfg = DynamicLlavaConfig(**{k: cfg_json[k] for k in keys if k in cfg_json and cfg_json[k] is not None},
                              vision=_vision_config(cfg_json))
     if cfg.num_key_value_heads != cfg.num_attention_heads:

@@ -310,3 +310,30 @@ def test_state_dict_contract_and_constants_match_reference_golden():
     assert mine == ref
     for k, v in g["constants"].items():
         assert getattr(C, k) == v, k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_reference_written_checkpoint_loads(tmp_path):
+    """a checkpoint directory produced by the REFERENCE classes (config.json from its DynamicLlavaConfig, weights = its model's own
+    state_dict in safetensors shards, CLIP tower directory; oracle/ref_save_checkpoint.py, run in a subprocess because the two `llava`
+    packages share a name) loads through this package's load_pretrained_model with identical tensors and the right configuration"""
+    import subprocess
+    import sys
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "oracle", "ref_save_checkpoint.py"), str(tmp_path)], capture_output=True, text=True,
+                       cwd=root, timeout=600)
+    assert r.returncode == 0 and "saved" in r.stdout, r.stderr[-2000:]
+    ck = str(tmp_path / "dynamic-llava-toy")
+    cj = json.load(open(os.path.join(ck, "config.json")))
+    assert cj["model_type"] == "dynamic_llava_llama" and "sparse_config" in cj
+    from llava.model.dynamic_llava_builder import load_pretrained_model
+    with pytest.warns(UserWarning, match="tokenizer"):
+        tok, model, proc, ctx = load_pretrained_model(ck, None, "dynamic-llava-toy", device="cpu")
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, 0).items()}
+    got = model.state_dict()
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    assert model.config.rope_theta == 10000.0 and model.config.sparse_config == cfg["sparse_config"]
+    assert model.config.mm_vision_select_layer == -2 and model.get_vision_tower().is_loaded and ctx == 2048 and proc is not None
