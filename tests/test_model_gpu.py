@@ -914,3 +914,29 @@ def test_full_size_7b_config1_against_cpu_oracle():
     assert first == int(pick[0, 0])  # generate() and the hand-rolled forward loop start from the same prefill
     print(f"config 1 @7B: max|gpu - oracle_fp32| = {err:.4f} (floor {floor:.4f}, scale {scale:.3f}); teacher-forced argmax agreement {agree:.2f}; "
           f"free-running tokens {free_gen[0].tolist()} vs oracle {o16['tokens'][0].tolist()}")
+
+
+@pytest.mark.parametrize("name", ["base", "truncate", "image_first", "image_last"])
+def test_prefill_edge_case_prompts_against_oracle(name):
+    """the whole sparsified prefill (all-position logits, KV lengths per layer class) on the prompt shapes of the prepare fixtures:
+    `tokenizer_model_max_length` cutting into the image span (15 of 16 image tokens survive -> k = 7), the placeholder right after BOS,
+    the placeholder as the last id (empty instruct span), under the oracle's own image mask"""
+    from oracle.cases import prepare_case_inputs
+    _, cfg, sd32, sd16, model, _, _ = _setup("toy_bf16_b2_forced")
+    ids, pix, kw = prepare_case_inputs(cfg, name)
+    model.config.tokenizer_model_max_length = kw.get("max_len")
+    e16, i16 = O.prepare_multimodal(sd16, cfg, ids, pix, **kw)
+    rec = {}
+    o16, past16 = O.llama_forward(sd16, cfg, inputs_embeds=e16, indices=i16, record=rec)
+    keep = rec["keep_index"]
+    e32, i32 = O.prepare_multimodal(sd32, cfg, ids, pix.float(), **kw)
+    o32, _ = O.llama_forward(sd32, cfg, inputs_embeds=e32, indices=i32, forced_keep_index=keep)
+    out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=keep)
+    got = out.logits.cpu()
+    assert got.shape == o32.shape, (got.shape, o32.shape)
+    floor = (o16 - o32).abs().max().item()
+    scale = o32.abs().max().item()
+    assert (got - o32).abs().max().item() <= 2 * floor + 1e-2 * scale
+    lens = torch.stack(list(out.past_key_values[1]), 0)
+    assert torch.equal(lens, torch.stack(list(past16[1]), 0))
+    model.config.tokenizer_model_max_length = None
