@@ -940,3 +940,30 @@ def test_prefill_edge_case_prompts_against_oracle(name):
     lens = torch.stack(list(out.past_key_values[1]), 0)
     assert torch.equal(lens, torch.stack(list(past16[1]), 0))
     model.config.tokenizer_model_max_length = None
+
+
+def test_dense_mode_predictors_switched_off_at_runtime():
+    """`use_vision_predictor=False` + `use_text_predictor=False` flipped on the live sparse_config (the dense LLaVA behaviour of the same
+    weights: no image drop, no decode decisions): every layer caches every token, logits follow the oracle run with the same flags"""
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b2_forced")
+    for c in (cfg["sparse_config"], model.config.sparse_config):
+        c["use_vision_predictor"] = False
+        c["use_text_predictor"] = False
+    n_new = 6
+    o16 = O.greedy_loop(sd16, cfg, ids, pix, n_new, per_sample=True)
+    o32 = O.greedy_loop(sd32, cfg, ids, pix.float(), n_new, per_sample=True, teacher_tokens=o16["tokens"])
+    got, past = _gpu_teacher_forced(model, {"n_new": n_new, "tokens": o16["tokens"]}, ids, pix, None, None)
+    floor = (o16["logits"] - o32["logits"]).abs().max().item()
+    scale = o32["logits"].abs().max().item()
+    assert (got - o32["logits"]).abs().max().item() <= 2 * floor + 1e-2 * scale
+    lens = torch.stack(list(past[1]), 0)
+    P = g["T"] - 1 + 16
+    assert lens.eq(P + n_new - 1).all()
+    toks = model.generate(ids, images=pix, max_new_tokens=n_new, do_sample=False, eos_token_id=None).cpu()
+    top2 = o32["logits"].topk(2, dim=-1).values
+    sure = ((top2[..., 0] - top2[..., 1]) > 4 * floor).T  # [B, n_new]
+    for b in range(g["B"]):
+        n = 0
+        while n < n_new and bool(sure[b, n]):
+            n += 1
+        assert toks[b, :n].tolist() == o16["tokens"][b, :n].tolist()
