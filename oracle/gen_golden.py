@@ -407,6 +407,33 @@ def host_prep_cases(out_dir):
     print("host prep:", len(res["prompts"]), "prompts,", len(res["token_ids"]), "tokenisations,", res["stopping"], res["model_names"])
 
 
+@torch.no_grad()
+def keep_rate_cases(out_dir, scratch):
+    """`vision_keep_rate` mutated on the live sparse_config between calls (bench_test/dynamic_llava_image_time_and_mem.py:63-65) at the
+    extremes the GPU tests visit: 1.0 (k = n_img: everything kept, still routed through the gather), 0.07 (k = 1), 0.0 (k = 0: the image
+    span vanishes), plus 0.3 (k = 4): prefill logits, keep index, KV lengths and one decode step."""
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = numpy_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd, torch.bfloat16, scratch)
+    model.model.config.sparse_config["use_output_text_predictor"] = False
+    ids, pix = synthetic_inputs(cfg, 2, 12, seed=1, dtype=torch.bfloat16)
+    res = {"preset": "toy", "B": 2, "T": 12, "weight_seed": 0, "input_seed": 1, "torch_version": str(torch.__version__), "rates": {}}
+    for rate in (1.0, 0.3, 0.07, 0.0):
+        model.model.config.sparse_config["vision_keep_rate"] = rate
+        try:
+            out = model(ids, images=pix, past_key_values=None)
+            nxt = out.logits[:, -1].argmax(-1).reshape(-1, 1)
+            out2 = model(nxt, images=None, past_key_values=out.past_key_values)
+            res["rates"][rate] = dict(logits=out.logits.clone(), step_logits=out2.logits.clone(),
+                                      kv_shapes=[k.shape[-2] for (k, v) in out2.past_key_values[0]])
+            print("keep rate", rate, tuple(out.logits.shape), res["rates"][rate]["kv_shapes"])
+        except Exception as e:  # noqa
+            res["rates"][rate] = {"raises": type(e).__name__}
+            print("keep rate", rate, "-> reference raises", type(e).__name__, str(e)[:120])
+    torch.save(res, os.path.join(out_dir, "keep_rates_bf16_b2.pt"))
+
+
 if __name__ == "__main__":
     only = [a for a in sys.argv[1:] if a.startswith("--only-")]
     if not only:
@@ -420,5 +447,7 @@ if __name__ == "__main__":
             host_prep_cases(os.path.join(ROOT, "tests", "golden"))
         if not only or "--only-prepare" in only:
             prepare_cases(os.path.join(ROOT, "tests", "golden"), scratch)
+        if not only or "--only-keeprates" in only:
+            keep_rate_cases(os.path.join(ROOT, "tests", "golden"), scratch)
         if not only or "--only-nocache" in only:
             nocache_case(os.path.join(ROOT, "tests", "golden"), scratch)

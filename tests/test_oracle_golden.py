@@ -260,3 +260,24 @@ def test_hf_warped_probs_match_installed_transformers(temperature, top_k, top_p)
     want = s.softmax(dim=-1)
     got = O.hf_warped_probs(logits, temperature, top_k, top_p)
     assert torch.equal(got, want), (got - want).abs().max()
+
+
+def test_keep_rate_extremes_match_reference_bitexact(golden_dir):
+    """vision_keep_rate mutated on the live config to 1.0 / 0.3 / 0.07 (k = 1) / 0.0 (k = 0): prefill logits at every position, one decode
+    step and the KV lengths per layer, bit for bit (the regimes tests/test_model_gpu.py::test_vision_keep_rate_extremes visits)"""
+    g = torch.load(os.path.join(golden_dir, "keep_rates_bf16_b2.pt"), weights_only=False)
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, seed=0).items()}
+    cfg["sparse_config"]["use_output_text_predictor"] = False
+    ids, pix = synthetic_inputs(cfg, g["B"], g["T"], seed=1, dtype=torch.bfloat16)
+    assert set(g["rates"]) == {1.0, 0.3, 0.07, 0.0}
+    for rate, ref in g["rates"].items():
+        assert "raises" not in ref
+        cfg["sparse_config"]["vision_keep_rate"] = rate
+        logits, past = O.model_forward(sd, cfg, ids, images=pix)
+        assert torch.equal(logits, ref["logits"]), rate
+        nxt = logits[:, -1].argmax(-1).reshape(-1, 1)
+        step, past = O.model_forward(sd, cfg, nxt, past=past)
+        assert torch.equal(step, ref["step_logits"]), rate
+        assert [k.shape[-2] for (k, v) in past[0]] == ref["kv_shapes"], rate
