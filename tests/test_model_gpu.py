@@ -967,3 +967,65 @@ def test_dense_mode_predictors_switched_off_at_runtime():
         while n < n_new and bool(sure[b, n]):
             n += 1
         assert toks[b, :n].tolist() == o16["tokens"][b, :n].tolist()
+
+
+def test_multiround_continuation_b2_ragged_per_sample():
+    """a new user turn (q_len = 5) over a cache whose per-sample lengths have diverged (B = 2, forced keep rates 0.3 / 0.7), then more
+    decode steps: every sample must behave exactly as if it ran alone (the default ragged semantics) — logits against the
+    per-sample oracle, per-layer KV lengths exact"""
+    g, cfg, sd32, sd16, model, ids, pix = _setup("toy_bf16_b2_forced", out_pred=True)
+    B = g["B"]
+    fd = g["forced_decisions"]  # [n, B]
+    cont, _ = synthetic_inputs(cfg, B, 12, seed=5, dtype=BF)
+    cont = cont[:, 6:11].contiguous()
+    n_pre, n_post = 4, 3
+
+    def oracle_run(sd, b, pixels, teacher=None):
+        rec = {}
+        logits, past = O.model_forward(sd, cfg, ids[b:b + 1], images=pixels[b:b + 1], record=rec,
+                                       forced_keep_index=None if teacher is None else teacher["keep"])
+        keep = rec["keep_index"]
+        outs, toks = [logits[:, -1]], []
+        step = 0
+        for phase, n in (("pre", n_pre), ("post", n_post)):
+            for t in range(n):
+                nxt = outs[-1].argmax(-1) if teacher is None else teacher["toks"][len(toks)]
+                toks.append(nxt)
+                logits, past = O.model_forward(sd, cfg, nxt.reshape(1, 1), past=past, forced_text_decision=fd[step, b].reshape(1, 1))
+                outs.append(logits[:, -1])
+                step += 1
+            if phase == "pre":
+                cl, past = O.model_forward(sd, cfg, cont[b:b + 1], past=past)
+                cont_logits = cl
+                outs.append(cl[:, -1])
+        return dict(keep=keep, toks=toks, outs=torch.cat(outs, 0), cont=cont_logits, lens=torch.stack(list(past[1]), 0))
+    o16 = [oracle_run(sd16, b, pix) for b in range(B)]
+    o32 = [oracle_run(sd32, b, pix.float(), teacher=o16[b]) for b in range(B)]
+    keep = torch.cat([o["keep"] for o in o16], 0)
+    out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=keep)
+    past = out.past_key_values
+    got, step, k = [out.logits[:, -1].cpu()], 0, 0
+    cont_got = None
+    for phase, n in (("pre", n_pre), ("post", n_post)):
+        for t in range(n):
+            cur = torch.stack([o16[b]["toks"][k] for b in range(B)], 0).reshape(B, 1)
+            out = model(cur.cuda(), past_key_values=past, forced_text_decision=fd[step])
+            past = out.past_key_values
+            got.append(out.logits[:, -1].cpu())
+            step += 1
+            k += 1
+        if phase == "pre":
+            out = model(cont.cuda(), past_key_values=past)
+            past = out.past_key_values
+            cont_got = out.logits.cpu()
+            got.append(cont_got[:, -1])
+    got = torch.stack(got, 0)  # [calls, B, V]
+    lens = torch.stack(list(past[1]), 0)  # [L, B]
+    for b in range(B):
+        floor = (o16[b]["outs"] - o32[b]["outs"]).abs().max().item()
+        scale = o32[b]["outs"].abs().max().item()
+        assert (got[:, b] - o32[b]["outs"]).abs().max().item() <= 2 * floor + 1e-2 * scale, b
+        cfloor = (o16[b]["cont"] - o32[b]["cont"]).abs().max().item()
+        assert (cont_got[b:b + 1] - o32[b]["cont"]).abs().max().item() <= 2 * cfloor + 1e-2 * scale, b
+        assert lens[:, b].tolist() == o16[b]["lens"][:, 0].tolist(), b
+    assert lens[-1, 0] != lens[-1, 1]  # the caches really diverged
