@@ -434,6 +434,46 @@ def keep_rate_cases(out_dir, scratch):
     torch.save(res, os.path.join(out_dir, "keep_rates_bf16_b2.pt"))
 
 
+@torch.no_grad()
+def multiround_b2_case(out_dir, scratch):
+    """the batched (B = 2) form of the second user turn: forced per-sample decisions (0.3 / 0.7) make the cached lengths diverge, so the
+    reference's B > 1 cache path runs — zero-padded stack per layer (cache_utils.py:165-241), then the 5-token turn appended BEHIND the
+    padding (plain `torch.cat`, :242-250) and unmasked attention over it.  Pins the oracle's batched-quirk mode there."""
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = numpy_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd, torch.bfloat16, scratch)
+    B = 2
+    ids, pix = synthetic_inputs(cfg, B, 12, seed=1, dtype=torch.bfloat16)
+    cont, _ = synthetic_inputs(cfg, B, 12, seed=5, dtype=torch.bfloat16)
+    cont = cont[:, 6:11].contiguous()
+    fd = forced_text_decisions(8, B, keep_rate=[0.3, 0.7], seed=3)
+    hs = force_hooks(model, None, list(fd))
+    snap = lambda o: torch.stack([x.clone() for x in o.past_key_values[1]], 0)
+    logits, lens, toks = [], [], []
+    out = model(ids, images=pix, past_key_values=None)
+    for t in range(4):
+        logits.append(out.logits[:, -1].clone()); lens.append(snap(out))
+        nxt = out.logits[:, -1].argmax(-1).reshape(B, 1); toks.append(nxt.reshape(-1).clone())
+        out = model(nxt, images=None, past_key_values=out.past_key_values)
+    logits.append(out.logits[:, -1].clone()); lens.append(snap(out))
+    out = model(cont, images=None, past_key_values=out.past_key_values)
+    cont_logits = out.logits.clone()
+    lens.append(snap(out))
+    for t in range(3):
+        nxt = out.logits[:, -1].argmax(-1).reshape(B, 1); toks.append(nxt.reshape(-1).clone())
+        out = model(nxt, images=None, past_key_values=out.past_key_values)
+        logits.append(out.logits[:, -1].clone()); lens.append(snap(out))
+    for h in hs:
+        h.remove()
+    res = dict(name="toy_bf16_b2_multiround", dtype="torch.bfloat16", B=B, T=12, weight_seed=0, input_seed=1, cont_ids=cont,
+               forced_decisions=fd, tokens=torch.stack(toks, 1), step_logits=torch.stack(logits, 0), cont_logits=cont_logits,
+               true_len_hist=torch.stack(lens, 0), preset="toy", torch_version=str(torch.__version__),
+               kv_shapes=torch.tensor([k.shape[-2] for (k, v) in out.past_key_values[0]]))
+    torch.save(res, os.path.join(out_dir, "multiround_bf16_b2.pt"))
+    print("multiround b2 tokens", res["tokens"].tolist(), "kv", res["kv_shapes"].tolist(), "true_len", res["true_len_hist"][-1].tolist())
+
+
 if __name__ == "__main__":
     only = [a for a in sys.argv[1:] if a.startswith("--only-")]
     if not only:
@@ -447,6 +487,8 @@ if __name__ == "__main__":
             host_prep_cases(os.path.join(ROOT, "tests", "golden"))
         if not only or "--only-prepare" in only:
             prepare_cases(os.path.join(ROOT, "tests", "golden"), scratch)
+        if not only or "--only-multiround-b2" in only:
+            multiround_b2_case(os.path.join(ROOT, "tests", "golden"), scratch)
         if not only or "--only-keeprates" in only:
             keep_rate_cases(os.path.join(ROOT, "tests", "golden"), scratch)
         if not only or "--only-nocache" in only:

@@ -281,3 +281,37 @@ def test_keep_rate_extremes_match_reference_bitexact(golden_dir):
         step, past = O.model_forward(sd, cfg, nxt, past=past)
         assert torch.equal(step, ref["step_logits"]), rate
         assert [k.shape[-2] for (k, v) in past[0]] == ref["kv_shapes"], rate
+
+
+def test_multiround_b2_batched_quirk_matches_reference_bitexact(golden_dir):
+    """B = 2 second user turn over diverged caches in the reference's own batched form: per-layer zero-padded stacks
+    (cache_utils.py:165-241), the 5-token turn appended behind the padding (:242-250), unmasked attention over it"""
+    g = torch.load(os.path.join(golden_dir, "multiround_bf16_b2.pt"), weights_only=False)
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, seed=0).items()}
+    B = g["B"]
+    ids, pix = synthetic_inputs(cfg, B, g["T"], seed=1, dtype=torch.bfloat16)
+    fd = g["forced_decisions"]
+    snap = lambda past: torch.stack(list(past[1]), 0)
+    logits, lens, toks, step = [], [], [], 0
+    out, past = O.model_forward(sd, cfg, ids, images=pix)
+    for t in range(4):
+        logits.append(out[:, -1]); lens.append(snap(past))
+        nxt = out[:, -1].argmax(-1).reshape(B, 1); toks.append(nxt.reshape(-1))
+        out, past = O.model_forward(sd, cfg, nxt, past=past, forced_text_decision=fd[step].reshape(B, 1))
+        step += 1
+    logits.append(out[:, -1]); lens.append(snap(past))
+    cont_logits, past = O.model_forward(sd, cfg, g["cont_ids"], past=past)
+    lens.append(snap(past))
+    out = cont_logits
+    for t in range(3):
+        nxt = out[:, -1].argmax(-1).reshape(B, 1); toks.append(nxt.reshape(-1))
+        out, past = O.model_forward(sd, cfg, nxt, past=past, forced_text_decision=fd[step].reshape(B, 1))
+        step += 1
+        logits.append(out[:, -1]); lens.append(snap(past))
+    assert torch.equal(torch.stack(toks, 1), g["tokens"])
+    assert torch.equal(torch.stack(lens, 0), g["true_len_hist"])
+    assert torch.equal(cont_logits, g["cont_logits"]) and torch.equal(torch.stack(logits, 0), g["step_logits"])
+    assert [k.shape[-2] for (k, v) in past[0]] == g["kv_shapes"].tolist()
+    assert g["true_len_hist"][-1][-1, 0] != g["true_len_hist"][-1][-1, 1]  # the lengths really diverged
