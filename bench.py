@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--out-keep", type=float, default=0.5, help="forced Bernoulli rate for output-token KV decisions; <0 disables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the decode step eagerly (for ncu launch lists)")
-    ap.add_argument("--cpu-new-tokens", type=int, default=4)
+    ap.add_argument("--cpu-new-tokens", type=int, default=32,
+                    help="greedy tokens per CPU-baseline step (B=1): CLIP + prefill + 31 decode steps, ~5-15 s of host work per step depending on "
+                         "the core count, so that `--impl reference --steps K --warmup W` still ends within a few minutes")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' times the same oracle port (the reference's PyTorch op sequence: eager torch, cuBLAS, "
                          "SDPA, torch.cat KV cache) on the GPU over the FULL workload — the like-for-like comparator of SURVEY.md §8d; the "
