@@ -326,6 +326,17 @@ def nocache_case(out_dir, scratch):
         out_all[variant] = dict(tokens=total[:, T:].clone(), last_logits=torch.stack(last_logits, 0), seq_lens=lens, final_logits=full,
                                 text_logits=seen, sparse_layer_inputs=sl_in, answer_indice=int(model.model.answer_indice))
         print("nocache", variant, "tokens", total[:, T:].tolist(), "lens", lens, "answer_indice", model.model.answer_indice)
+    # branch precedence (dynamic_modeling_llama.py:2261 before :2393): with the instruct predictor on, a use_cache=False call drops
+    # instruction tokens and never reaches the output-thinning branch (B == 1 asserted by the reference)
+    cfg_i = preset("toy")
+    cfg_i["sparse_config"]["use_output_text_predictor"] = True
+    cfg_i["sparse_config"]["use_instruct_predictor"] = True
+    model_i = build_reference(cfg_i, numpy_state_dict(cfg_i, seed=0), torch.bfloat16, scratch)
+    ids_i, pix_i = synthetic_inputs(cfg_i, 1, 20, seed=1, dtype=torch.bfloat16)
+    tot = torch.cat([ids_i, torch.tensor([[7, 9, 11]])], dim=1)
+    out_i = model_i(tot, images=pix_i, past_key_values=None, input_embeds_indices=None, use_cache=False)
+    out_all["instruct_precedence"] = dict(ids=tot, logits=out_i.logits.clone(), answer_indice=model_i.model.answer_indice)
+    print("nocache + instruct predictor: logits", tuple(out_i.logits.shape), "answer_indice", model_i.model.answer_indice)
     res = dict(name="toy_bf16_b2_nocache", dtype="torch.bfloat16", B=B, T=T, n_calls=n_calls, weight_seed=0, input_seed=1,
                forced_logits=forced, preset="toy", torch_version=torch.__version__, **out_all)
     torch.save(res, os.path.join(out_dir, "nocache_bf16_b2.pt"))

@@ -1029,3 +1029,28 @@ def test_multiround_continuation_b2_ragged_per_sample():
         assert (cont_got[b:b + 1] - o32[b]["cont"]).abs().max().item() <= 2 * cfloor + 1e-2 * scale, b
         assert lens[:, b].tolist() == o16[b]["lens"][:, 0].tolist(), b
     assert lens[-1, 0] != lens[-1, 1]  # the caches really diverged
+
+
+def test_nocache_with_instruct_predictor_takes_the_instruct_branch():
+    """elif precedence of the reference (dynamic_modeling_llama.py:2261 before :2393), pinned by the `instruct_precedence` entry of
+    tests/golden/nocache_bf16_b2.pt: with the instruct predictor on, a `use_cache=False` call drops instruction tokens and never thins
+    generated ones; decisions pinned to the reference's through the predictor hook, image mask from the oracle"""
+    g = torch.load(os.path.join(GOLD, "nocache_bf16_b2.pt"), weights_only=False)["instruct_precedence"]
+    cfg, sd16, model = _instruct_model()
+    _, pix = synthetic_inputs(cfg, 1, 20, seed=1, dtype=BF)
+    rec = {}
+    ref, past = O.model_forward(sd16, cfg, g["ids"], images=pix, use_cache=False, state={"answer_indice": None}, record=rec)
+    assert torch.equal(ref, g["logits"])
+    dec = rec["instruct_logits"][0, :, 0] > rec["instruct_logits"][0, :, 1]
+
+    def hook(mod, args, out):
+        z = torch.zeros_like(out)
+        z[..., 0] = torch.where(dec.to(out.device).reshape(out.shape[:-1]), 1.0, -1.0).to(out.dtype)
+        return z
+    h = model.model.instruct_score_predictor.register_forward_hook(hook)
+    out = model(g["ids"].cuda(), images=pix.cuda(), use_cache=False, forced_keep_index=rec["keep_index"])
+    h.remove()
+    assert out.past_key_values is None and model.model.answer_indice is None
+    assert out.logits.shape == g["logits"].shape
+    scale = g["logits"].abs().max().item()
+    assert (out.logits.cpu() - g["logits"]).abs().max().item() < 0.04 * scale

@@ -315,3 +315,18 @@ def test_multiround_b2_batched_quirk_matches_reference_bitexact(golden_dir):
     assert torch.equal(cont_logits, g["cont_logits"]) and torch.equal(torch.stack(logits, 0), g["step_logits"])
     assert [k.shape[-2] for (k, v) in past[0]] == g["kv_shapes"].tolist()
     assert g["true_len_hist"][-1][-1, 0] != g["true_len_hist"][-1][-1, 1]  # the lengths really diverged
+
+
+def test_nocache_with_instruct_predictor_takes_the_instruct_branch(golden_dir):
+    """elif precedence of the reference (dynamic_modeling_llama.py:2261 before :2393): `use_cache=False` with the instruct predictor on drops
+    instruction tokens at the prefill and never thins the generated tokens; `answer_indice` stays None"""
+    g = torch.load(os.path.join(golden_dir, "nocache_bf16_b2.pt"), weights_only=False)["instruct_precedence"]
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    cfg["sparse_config"]["use_instruct_predictor"] = True
+    sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, seed=0).items()}
+    _, pix = synthetic_inputs(cfg, 1, 20, seed=1, dtype=torch.bfloat16)
+    state = {"answer_indice": None}
+    logits, past = O.model_forward(sd, cfg, g["ids"], images=pix, use_cache=False, state=state)
+    assert past is None and state["answer_indice"] is None and g["answer_indice"] is None
+    assert torch.equal(logits, g["logits"])
