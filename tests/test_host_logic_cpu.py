@@ -337,3 +337,23 @@ def test_reference_written_checkpoint_loads(tmp_path):
     assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
     assert model.config.rope_theta == 10000.0 and model.config.sparse_config == cfg["sparse_config"]
     assert model.config.mm_vision_select_layer == -2 and model.get_vision_tower().is_loaded and ctx == 2048 and proc is not None
+
+
+def test_eval_driver_import_surface():
+    """every `llava.*` import of the reference's llava/dynamic_eval/*.py drivers resolves against this repo's shim package
+    (model_vqa_loader.py:1-20): utils.disable_torch_init, the builder, mm_utils, conversation, constants"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch\n"
+            "from llava.utils import disable_torch_init\n"
+            "from llava.model.dynamic_llava_builder import load_pretrained_model\n"
+            "from llava.mm_utils import tokenizer_image_token, process_images, get_model_name_from_path, KeywordsStoppingCriteria\n"
+            "from llava.conversation import conv_templates, SeparatorStyle\n"
+            "from llava.constants import IMAGE_TOKEN_INDEX, DEFAULT_IMAGE_TOKEN, DEFAULT_IM_START_TOKEN, DEFAULT_IM_END_TOKEN, IMAGE_PLACEHOLDER\n"
+            "from llava.model import DynamicLlavaLlamaForCausalLM, LlavaLlamaForCausalLM\n"
+            "import llava; assert 'reference' not in llava.__file__\n"
+            "disable_torch_init(); l = torch.nn.Linear(4, 4); assert l.weight.shape == (4, 4)\n"
+            "print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)  # own process: it patches torch.nn
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-1500:]
