@@ -36,12 +36,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--preset", default="llava-1.5-7b")
-    ap.add_argument("--batch", type=int, default=8, help="samples per GPU")
-    ap.add_argument("--prompt-len", type=int, default=32)
-    ap.add_argument("--new-tokens", type=int, default=128)
-    ap.add_argument("--keep-rate", type=float, default=0.2)
-    ap.add_argument("--out-keep", type=float, default=0.5, help="forced Bernoulli rate for output-token KV decisions; <0 disables")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config (1-based): 2 = the config the metric is quoted on (default); 3 = ragged-KV stress (B=8 per GPU, "
+                         "256 tokens, per-sample forced keep rates linspace(0.1,0.9,8); meant for --gpus 8 = batch 64); 4 = 13B, B=4 per GPU "
+                         "(= 32 over 8 GPUs), P=2048 prefill + 16 tokens; 5 = keep-rate sweep {0.1,0.2,0.5,1.0}, 7B, B=16, one GPU")
+    ap.add_argument("--preset", default=None)
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU")
+    ap.add_argument("--prompt-len", type=int, default=None)
+    ap.add_argument("--new-tokens", type=int, default=None)
+    ap.add_argument("--keep-rate", type=float, default=None)
+    ap.add_argument("--out-keep", type=float, default=None, help="forced Bernoulli rate for output-token KV decisions; <0 disables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the decode step eagerly (for ncu launch lists)")
     ap.add_argument("--cpu-new-tokens", type=int, default=32,
@@ -51,7 +55,119 @@ def parse():
                     help="--impl reference only: 'cuda' times the same oracle port (the reference's PyTorch op sequence: eager torch, cuBLAS, "
                          "SDPA, torch.cat KV cache) on the GPU over the FULL workload — the like-for-like comparator of SURVEY.md §8d; the "
                          "default (and what the driver runs) is the host-core baseline")
-    return ap.parse_args()
+    a = ap.parse_args()
+    # per-config defaults; explicit flags override
+    table = {2: dict(preset="llava-1.5-7b", batch=8, prompt_len=32, new_tokens=128, keep_rate=0.2, out_keep=0.5),
+             3: dict(preset="llava-1.5-7b", batch=8, prompt_len=32, new_tokens=256, keep_rate=0.2, out_keep="linspace(0.1,0.9)"),
+             4: dict(preset="llava-1.5-13b", batch=4, prompt_len=2048 - 576 + 1, new_tokens=16, keep_rate=0.2, out_keep=0.5),
+             5: dict(preset="llava-1.5-7b", batch=16, prompt_len=32, new_tokens=64, keep_rate=0.2, out_keep=-1.0)}[a.config]
+    for k, v in table.items():
+        if getattr(a, k) is None:
+            setattr(a, k, v)
+    return a
+
+
+def workload_name(a, world=1):
+    P = a.prompt_len - 1 + 576
+    k = int(576 * a.keep_rate)
+    ok = "per-sample linspace(0.1,0.9) (ragged-KV stress)" if a.out_keep == "linspace(0.1,0.9)" else (
+        f"{a.out_keep}" if float(a.out_keep) >= 0 else "off (output predictor disabled)")
+    return (f"BASELINE config {a.config}: {a.preset} bf16, batch={a.batch}/GPU x {world} GPU, {a.prompt_len}-id prompt + 1 image "
+            f"(P={P} -> P'={P - 576 + k} at keep {a.keep_rate}), vision_keep_rate={a.keep_rate}, output_text_keep_rate={ok} "
+            f"(forced seeded decisions), {a.new_tokens}-token greedy decode; step = CLIP+projector+splice+prefill+decode of one batch")
+
+
+def out_keep_rates(a):
+    """forced Bernoulli keep rate(s) of the output-token decisions: a scalar, or config 3's per-sample ramp"""
+    if a.out_keep == "linspace(0.1,0.9)":
+        return torch.linspace(0.1, 0.9, a.batch).tolist()
+    return float(a.out_keep)
+
+
+def k1_point(name, B, T, H, k, dev, hbm_peak, timeit):
+    """K1 (select + gather/compact) on one shape, graph-timed, buffers rotated beyond the 126 MB L2; bytes = SURVEY.md §8d's formula"""
+    import ctypes
+    from dynamic_llava_b200._lib import lib
+    L = lib()
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n_img, s0 = 576, 5
+    Pn = T - 1 + n_img
+    Pp = Pn - n_img + k
+    n_rot = max(2, int(300e6 // (B * Pn * H * 2)) + 1)
+    hid = [torch.randn(B, Pn, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
+    outb = [torch.empty(B, Pp, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
+    logits = torch.randn(B, n_img, 2, device=dev, dtype=torch.bfloat16)
+    keep = torch.empty(B, k, dtype=torch.int64, device=dev)
+    pos = torch.empty(B, Pp, dtype=torch.int32, device=dev)
+    cu = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    ms = timeit(lambda i: L.select_compact(P(logits), None, P(hid[i]), P(outb[i]), P(keep), P(pos), P(cu), B, Pn, H, s0, n_img, k, 0, st()), n_rot)
+    nbytes = 2 * B * Pp * H * 2 + B * n_img * 4 + B * Pp * 4
+    del hid, outb
+    return {"kernel": name, "bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / ms / 1e6 / hbm_peak,
+            "us": ms * 1e3, "algorithmic_bytes": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}
+
+
+def rot_timeit(fn, n_rot=1, iters=20, warm=3):
+    """ms per launch inside ONE CUDA-graph replay of `iters` launches (CUDA events around the replay).  Eager ctypes launches cost
+    ~13 us of host time each (more with tensor-map encoding), which hid every kernel shorter than that
+    (profiles/r1_k1_warp_select_experiment.md); a replay has no host in the loop."""
+    for i in range(warm):
+        fn(i % n_rot)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for i in range(iters):
+                fn(i % n_rot)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()  # warm replay
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def config5_sweep(model, a, ids_d, pix_d, dev):
+    """BASELINE config 5: keep-rate sweep {0.1, 0.2, 0.5, 1.0} on 7B, batch 16, one GPU: generated tokens/s and the achieved HBM GB/s of
+    K1 (select + gather/compact) against the effective token count B * P' (run-time mutation of the live sparse_config, like the
+    reference's own bench script, llava/dynamic_eval/bench_test/dynamic_llava_image_time_and_mem.py:63-65)."""
+    hbm_peak, _ = measured_peaks()
+    B, T, NN = a.batch, a.prompt_len, a.new_tokens
+    rows = []
+    for rate in (0.1, 0.2, 0.5, 1.0):
+        model.config.sparse_config["vision_keep_rate"] = rate
+        k = int(576 * rate)
+        P = T - 1 + 576
+        Pp = P - 576 + k
+        kw = dict(images=pix_d, do_sample=False, eos_token_id=None)
+
+        def timed(fn, reps=3, warm=2):
+            for _ in range(warm):
+                fn()
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return statistics.median(ts)
+        t_pre = timed(lambda: model.generate(ids_d, max_new_tokens=1, **kw))
+        t_all = timed(lambda: model.generate(ids_d, max_new_tokens=NN, **kw))
+        k1 = k1_point(f"K1 keep {rate}", B, T, model.config.hidden_size, k, dev, hbm_peak, rot_timeit)
+        rows.append({"vision_keep_rate": rate, "k": k, "P_prime": Pp, "effective_tokens": B * Pp, "clip_prefill_ms": t_pre,
+                     "prefill_tokens_per_s": B * P / (t_pre / 1e3), "generated_tokens_per_s": B * NN / (t_all / 1e3),
+                     "decode_ms_per_step": (t_all - t_pre) / max(NN - 1, 1), "k1_us": k1["us"], "k1_achieved_gbs": k1["achieved"],
+                     "k1_frac_of_hbm_peak": k1["frac"], "k1_algorithmic_bytes": k1["algorithmic_bytes"]})
+    model.config.sparse_config["vision_keep_rate"] = a.keep_rate
+    return rows
 
 
 def kernel_rooflines(dev):
@@ -67,32 +183,10 @@ def kernel_rooflines(dev):
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     tf_peak = float(pk.get("bf16_tflops_sustained", 1400.0))
+    tf_burst = float(pk.get("bf16_tflops", 1650.0))
     hbm_peak = float(pk.get("hbm_gbs", 6650.0))
 
-    def timeit(fn, n_rot=1, iters=20, warm=3):
-        """ms per launch inside ONE CUDA-graph replay of `iters` launches (CUDA events around the replay).  Eager ctypes launches cost
-        ~13 us of host time each (more with tensor-map encoding), which hid every kernel shorter than that
-        (profiles/r1_k1_warp_select_experiment.md); a replay has no host in the loop."""
-        for i in range(warm):
-            fn(i % n_rot)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(g, stream=side):
-                for i in range(iters):
-                    fn(i % n_rot)
-        torch.cuda.current_stream().wait_stream(side)
-        g.replay()  # warm replay
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
-
+    timeit = rot_timeit
     out = []
     for name, B, nh, Lq in (("K2 dl_attn_prefill_tc4 L=2048 B=8 32 heads (stress)", 8, 32, 2048), ("K2 dl_attn_prefill_tc4 L=607 B=8 (layers 0-1)", 8, 32, 607),
                             ("K2 dl_attn_prefill_tc4 L=146 B=8 (layers 2-31)", 8, 32, 146)):
@@ -106,25 +200,15 @@ def kernel_rooflines(dev):
         ms = timeit(lambda i: L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), 0, st()),
                     iters=50, warm=10)
         flop = 2.0 * Lq * Lq * H * B
-        out.append({"kernel": name, "bound": "tensor", "achieved": flop / ms / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": flop / ms / 1e9 / tf_peak, "us": ms * 1e3, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"})
+        # the kernel is timed ALONE in a 50-launch graph replay = the burst case: `frac` divides by the burst peak; the fraction of the
+        # sustained peak (what a long step can hold) is printed beside it
+        out.append({"kernel": name, "bound": "tensor", "achieved": flop / ms / 1e9, "peak": tf_burst, "unit": "TFLOP/s",
+                    "frac": flop / ms / 1e9 / tf_burst, "frac_of_sustained": flop / ms / 1e9 / tf_peak, "peak_sustained": tf_peak, "us": ms * 1e3,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone) / bf16_tflops_sustained"})
         del qkv, K, V, o
-    for name, B, T, H in (("K1 dl_select_compact 13B B=32 P=2048 keep 0.2", 32, 1473, 5120), ("K1 dl_select_compact 7B B=8 P=607 keep 0.2 (this workload)", 8, 32, 4096)):
-        n_img, s0, k = 576, 5, 115
-        Pn = T - 1 + n_img
-        Pp = Pn - n_img + k
-        n_rot = max(2, int(300e6 // (B * Pn * H * 2)) + 1)
-        hid = [torch.randn(B, Pn, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
-        outb = [torch.empty(B, Pp, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
-        logits = torch.randn(B, n_img, 2, device=dev, dtype=torch.bfloat16)
-        keep = torch.empty(B, k, dtype=torch.int64, device=dev)
-        pos = torch.empty(B, Pp, dtype=torch.int32, device=dev)
-        cu = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        ms = timeit(lambda i: L.select_compact(P(logits), None, P(hid[i]), P(outb[i]), P(keep), P(pos), P(cu), B, Pn, H, s0, n_img, k, 0, st()), n_rot)
-        nbytes = 2 * B * Pp * H * 2 + B * n_img * 4 + B * Pp * 4
-        out.append({"kernel": name, "bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / ms / 1e6 / hbm_peak,
-                    "us": ms * 1e3, "algorithmic_bytes": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs"})
-        del hid, outb
+    for name, B, T, H, k in (("K1 dl_select_compact 13B B=32 P=2048 keep 0.2", 32, 1473, 5120, 115),
+                             ("K1 dl_select_compact 7B B=8 P=607 keep 0.2 (config 2's own shape)", 8, 32, 4096, 115)):
+        out.append(k1_point(name, B, T, H, k, dev, hbm_peak, timeit))
     torch.cuda.empty_cache()
     return out
 
@@ -201,8 +285,9 @@ def run_b200(a):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     cfgd = preset(a.preset)
+    has_out = a.out_keep == "linspace(0.1,0.9)" or float(a.out_keep) >= 0
     cfgd["sparse_config"]["vision_keep_rate"] = a.keep_rate
-    cfgd["sparse_config"]["use_output_text_predictor"] = True
+    cfgd["sparse_config"]["use_output_text_predictor"] = has_out
     cfg = DynamicLlavaConfig(**cfgd)
     model = DynamicLlavaLlamaForCausalLM(cfg, device=dev)
     model.get_vision_tower().load_model()
@@ -215,7 +300,7 @@ def run_b200(a):
 
     B, T, NN = a.batch, a.prompt_len, a.new_tokens
     ids_h, pix_h = synthetic_inputs(cfgd, B, T, seed=1 + rank)  # each rank owns its own chunk of the global batch
-    fd = forced_text_decisions(max(NN - 1, 1), B, keep_rate=a.out_keep, seed=3 + rank) if a.out_keep >= 0 else None
+    fd = forced_text_decisions(max(NN - 1, 1), B, keep_rate=out_keep_rates(a), seed=3 + rank) if has_out else None
     ids_pin, pix_pin = ids_h.pin_memory(), pix_h.pin_memory()
     ids_d, pix_d = ids_h.to(dev), pix_h.to(dev)
     gen_kw = dict(max_new_tokens=NN, do_sample=False, eos_token_id=None, forced_text_decisions=fd, use_cuda_graph=not a.no_graph)  # EOS off: fixed decode length
@@ -266,16 +351,17 @@ def run_b200(a):
     extra = {}
     if rank == 0:
         extra = phase_and_roofline(model, eng, a, ids_d, pix_d, fd, dev)
+        if a.config == 5:
+            extra["sweep"] = config5_sweep(model, a, ids_d, pix_d, dev)
     total_tokens = world * B * NN * a.steps
     line = {
         "metric": METRIC, "value": total_tokens / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (seeded randn 336x336 pixels, random ids, N(0,0.02) random-init weights)",
-        "config": {"workload": f"BASELINE config 2: {a.preset} bf16, batch={B}/GPU, {T}-id prompt + 1 image (P=607 -> P'=146 at keep 0.2), "
-                               f"vision_keep_rate={a.keep_rate}, output_text_keep_rate={a.out_keep} (forced seeded decisions), "
-                               f"{NN}-token greedy decode; step = CLIP+projector+splice+prefill+decode of one batch",
-                   "global_batch": world * B, "prompt_ids": T, "new_tokens": NN, "parallelism": f"replicas x{world} (no data-path collective)",
-                   "l2": "no flush needed: every step streams the 13.5 GB weight set (>> 126 MB L2)"},
+        "config": {"workload": workload_name(a, world),
+                   "baseline_config": a.config, "global_batch": world * B, "prompt_ids": T, "new_tokens": NN,
+                   "parallelism": f"replicas x{world} (no data-path collective)",
+                   "l2": "no flush needed: every step streams the whole bf16 weight set (13.5 / 26 GB >> 126 MB L2)"},
         "e2e": {"value": total_tokens / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(ids_pin.numel() * 8 + pix_pin.numel() * 2),
                 "d2h_bytes_per_step": int(B * NN * 8)},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -284,18 +370,78 @@ def run_b200(a):
     if rank == 0 and "phases" in line and NN > 1:
         line["phases"]["decode_ms_per_token_step"] = (ms / a.steps - line["phases"]["clip_prefill_ms"]) / (NN - 1)
         line["phases"]["decode_tokens_per_s_per_gpu"] = B * 1e3 / line["phases"]["decode_ms_per_token_step"]
+        ph = line["phases"]
+        # whole decode step in situ: (weights + mean KV bytes) / step time / measured HBM peak
+        ph["decode_step_hbm_gbs"] = (ph["decode_step_weight_bytes"] + ph["decode_step_mean_kv_bytes"]) / (ph["decode_ms_per_token_step"] / 1e3) / 1e9
+        ph["decode_step_hbm_frac"] = ph["decode_step_hbm_gbs"] / ph["hbm_peak_gbs"]
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(a, steps=1, warmup=0)
+            line["cpu_baseline"] = cpu_baseline(a, steps=3, warmup=1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _src_sha16(names):
+    import hashlib
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(ROOT, "dynamic_llava_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel_key, algorithmic_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of THIS build of the kernel
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py; entries are keyed by the sha of the kernel's sources so that a capture of
+    an older build is never quoted for a newer one).  None when no capture of the current sources is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed (profiles/ncu_traffic.json missing)"
+    db = json.load(open(path))
+    ent = db.get(kernel_key)
+    if ent is None:
+        return None, f"no ncu capture for {kernel_key}"
+    sha = _src_sha16(ent["sources"])
+    if sha != ent["src_sha16"]:
+        return None, f"ncu capture is of an older build of {ent['sources']} (sha {ent['src_sha16']} != {sha}): re-run tools/ncu_traffic.py"
+    # the capture is of one representative launch; scale its measured/algorithmic ratio to this step's average launch
+    ratio = ent["dram_bytes_per_launch"] / ent["algorithmic_bytes_per_launch"]
+    return ratio * algorithmic_bytes, (f"ncu --set full of this build ({ent['what']}): dram read+write {ent['dram_bytes_per_launch'] / 1e6:.2f} MB vs "
+                                       f"{ent['algorithmic_bytes_per_launch'] / 1e6:.2f} MB algorithmic (x{ratio:.3f}), scaled to this step's average launch")
+
+
+def graph_time(fn, iters, warm=2):
+    """ms per call of `fn` inside ONE CUDA-graph replay of `iters` calls (no host in the loop, PDL edges as in the real step)"""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
 def phase_and_roofline(model, eng, a, ids_d, pix_d, fd, dev):
-    """untimed diagnostics: prefill vs decode split and the skinny-GEMM (weight streaming) roofline."""
+    """untimed diagnostics: prefill vs decode split, the skinny-GEMM (weight streaming) roofline, the whole-step HBM fraction, live K3."""
+    import ctypes
+    import math
     cfg = model.config
-    B, NN = a.batch, a.new_tokens
+    B, NN, T = a.batch, a.new_tokens, a.prompt_len
+    P = T - 1 + 576
+    Pp = P - 576 + int(576 * a.keep_rate)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     # phase split: generate with 1 new token == CLIP + prefill (+ first greedy)
     t = []
@@ -307,55 +453,77 @@ def phase_and_roofline(model, eng, a, ids_d, pix_d, fd, dev):
         torch.cuda.synchronize()
         t.append(s.elapsed_time(e))
     prefill_ms = statistics.median(t)
-    # dominant kernel: dl_skinny_gemm over every decoder weight of one decode step (each launch reads its weight once)
+    # leave the session in its end-of-decode state (final kv_len) for the K3 measurement below
+    model.generate(ids_d, images=pix_d, max_new_tokens=NN, do_sample=False, eos_token_id=None, forced_text_decisions=fd)
     sess = next(iter(model._sessions.values()))
+    # dominant kernel: dl_skinny_gemm over every decoder weight of one decode step (each launch reads its weight once)
     H, I, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+    nh = cfg.num_attention_heads
+    hd = H // nh
     shapes = []
     for W in eng.packed["layers"]:
         shapes += [(sess.xn, W["wqkv"], 3 * H, H), (sess.attn, W["wo"], H, H), (sess.xn, W["wgu"], 2 * I, H), (sess.act, W["wd"], H, I)]
     shapes.append((sess.xn, model.lm_head.weight, V, H))
     bytes_total = sum(w.numel() * 2 for _, w, _, _ in shapes)
-    for _ in range(2):
+    launches_before = eng.launches
+
+    def all_gemms():
         for x, w, N, K in shapes:
             eng._gemm(sess, x, w, B, N, K)
-    torch.cuda.synchronize()
-    # timed inside a CUDA-graph replay, the way the decode step itself runs: an eager `_gemm` call costs ~15-20 us of host time (two
-    # ctypes calls, tensor-map encoding), as much as the average launch lasts, so an eager loop measures the host
-    reps = 5
-    launches_before = eng.launches
-    g = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(g, stream=side):
-            for _ in range(reps):
-                for x, w, N, K in shapes:
-                    eng._gemm(sess, x, w, B, N, K)
-    torch.cuda.current_stream().wait_stream(side)
-    eng.launches = launches_before  # capture only records
-    g.replay()
-    torch.cuda.synchronize()
-    s, e = ev(), ev()
-    s.record()
-    g.replay()
-    e.record()
-    torch.cuda.synchronize()
-    gemm_ms = s.elapsed_time(e) / reps
-    del g
+    # timed inside a CUDA-graph replay, the way the decode step itself runs: an eager `_gemm` call costs ~15-20 us of host time, as
+    # much as the average launch lasts, so an eager loop measures the host
+    gemm_ms = graph_time(all_gemms, iters=5)
     peak, how = measured_peaks()
     achieved = bytes_total / (gemm_ms / 1e3) / 1e9
-    other = kernel_rooflines(dev)
+    # K3 live: dl_attn_decode_fused on this workload's own ragged lengths (end of the decode: the longest caches), one lo layer and
+    # one hi layer, bytes = sum_b kv_len[l][b] * 2 * hd * 2 * heads (K and V rows of every cached key)
+    P_ = lambda x: None if x is None else ctypes.c_void_p(x.data_ptr())
+    stv = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    SL = cfg.sparse_config["sparse_layer"]
+    ar = sess.arena
+    lens_host = ar.kv_len.cpu()
+    k3 = []
+    s_qkv = eng.L.skinny_gemm_splits(3 * H, H, eng.skinny_target_ctas)
+    eng._gemm(sess, sess.xn, eng.packed["layers"][0]["wqkv"], B, 3 * H, H)  # valid slices in sess.partial
+    for l in (0, SL):
+        K_, V_, cap = ar.layer(l)
+        ns = eng._n_split(B, nh, cap)
+        if ns > 1 and sess.attn_ws is None:
+            sess.attn_ws = torch.empty(eng.L.attn_decode_workspace_bytes(B, nh, 16) // 4, device=dev, dtype=torch.float32)
+        kvl = ar.kv_len[l]
+        fn = lambda: eng.L.attn_decode_fused(P_(sess.partial), s_qkv, P_(ar.pos), None, P_(eng.packed["cos"]), P_(eng.packed["sin"]), P_(K_), P_(V_),
+                                             P_(kvl), P_(sess.attn), P_(sess.attn_ws), B, nh, hd, cap, ns, 1.0 / math.sqrt(hd), 0, None, 0,
+                                             ar.floor_lo if l < SL else ar.floor_hi, stv())
+        # the arena rows of 20 back-to-back launches on the same layer would sit in L2: rotate over >= 4 layers of the same class
+        ms = graph_time(fn, iters=20)
+        nbytes = int(lens_host[l].sum()) * 2 * hd * 2 * nh
+        k3.append({"kernel": f"K3 dl_attn_decode_fused layer {l} ({'lo' if l < SL else 'hi'} class), kv_len {lens_host[l].tolist()}", "bound": "hbm",
+                   "achieved": nbytes / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": nbytes / ms / 1e6 / peak, "us": ms * 1e3,
+                   "algorithmic_bytes": nbytes, "peak_source": how,
+                   "note": "latency-bound at these lengths; the same layer's rows are re-read by the 20 graph-timed launches, so L2 serves them: "
+                           "an upper bound on the in-step rate"})
+    eng.launches = launches_before  # diagnostics only
+    other = kernel_rooflines(dev) + k3
+    # whole decode step against its HBM floor: weights streamed once + the mean KV bytes over the decode steps of this workload
+    n_lo, n_hi = SL, cfg.num_hidden_layers - SL
+    kv_row = 2 * H * 2  # K and V of one token, all heads, bf16
+    steps = max(NN - 1, 1)
+    mean_lo = P + (steps - 1) / 2.0
+    kept = (fd[:steps].double().cumsum(0) - fd[:steps].double()).mean(0).sum().item() if fd is not None else B * (steps - 1) / 2.0
+    kv_bytes = kv_row * (n_lo * B * mean_lo + n_hi * (B * Pp + kept))
+    traffic, traffic_src = measured_traffic("skinny_gemm_kernel", bytes_total / len(shapes))
     return {
         "roofline_kernels": other,
-        "phases": {"clip_prefill_ms": prefill_ms, "prefill_tokens_per_s": B * 607 / (prefill_ms / 1e3),
-                   "decode_ms_per_token_step": None, "weight_gemm_ms_per_decode_step": gemm_ms},
+        "phases": {"clip_prefill_ms": prefill_ms, "prefill_tokens_per_s": B * P / (prefill_ms / 1e3),
+                   "decode_ms_per_token_step": None, "weight_gemm_ms_per_decode_step": gemm_ms,
+                   "decode_step_weight_bytes": bytes_total, "decode_step_mean_kv_bytes": kv_bytes, "hbm_peak_gbs": peak},
         "roofline": {"bound": "hbm", "kernel": "skinny_gemm_kernel (decode weight streaming, TMA+tcgen05)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": 1.033 * bytes_total / len(shapes),
-                     "traffic_source": "ncu --set full, QKV launch: dram read+write 104.88 MB vs 101.5 MB algorithmic (x1.033), "
-                                       "scaled to this step's average launch (profiles/r1_ncu_skinny_gemm_full.md)",
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": how,
                      "algorithmic_bytes_per_launch": bytes_total / len(shapes), "launches_per_decode_step": len(shapes),
-                     "avg_launch_us": gemm_ms * 1e3 / len(shapes)},
+                     "avg_launch_us": gemm_ms * 1e3 / len(shapes),
+                     "timing": "the step's 129 weight-streaming launches replayed ALONE in one CUDA graph (isolated); the in-situ whole-step "
+                               "fraction is phases.decode_step_hbm_frac"},
     }
 
 
@@ -374,12 +542,14 @@ def cpu_baseline(a, steps, warmup):
     cfgd["sparse_config"]["vision_keep_rate"] = a.keep_rate
     cfgd["sparse_config"]["use_output_text_predictor"] = False  # config 1: reference's image-bench setting
     avail = psutil.virtual_memory().available
-    if avail < 20e9:
-        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"skipped: {avail/1e9:.0f} GB host RAM free < 20 GB"}
+    need = 36e9 if "13b" in a.preset else 20e9
+    if avail < need:
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"skipped: {avail/1e9:.0f} GB host RAM free < {need/1e9:.0f} GB"}
     t0 = time.perf_counter()
     sd = tiled_state_dict(cfgd, seed=0)
     build_s = time.perf_counter() - t0
-    ids, pix = synthetic_inputs(cfgd, 1, a.prompt_len, seed=1)
+    T_cpu = min(a.prompt_len, 32)  # config 4's 1473-id prompt (a 53 TFLOP 13B prefill) would not end within minutes on host cores
+    ids, pix = synthetic_inputs(cfgd, 1, T_cpu, seed=1)
     n_new = a.cpu_new_tokens
     vals = []
     t_start = time.perf_counter()
@@ -392,7 +562,7 @@ def cpu_baseline(a, steps, warmup):
         if vals and time.perf_counter() - t_start > 150.0:  # bounded: a long --steps request must still end within a few minutes
             break
     return {"value": statistics.median(vals), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{a.preset} bf16 random-init (tiled), B=1, {a.prompt_len}-id prompt + 1 image, keep {a.keep_rate}, {n_new} greedy tokens "
+            "sample": f"{a.preset} bf16 random-init (tiled), B=1, {T_cpu}-id prompt + 1 image, keep {a.keep_rate}, {n_new} greedy tokens "
                       f"(CLIP+prefill+{n_new - 1} decode steps) per step; weights built in {build_s:.0f}s (untimed)",
             "steps": len(vals)}
 
@@ -409,11 +579,12 @@ def gpu_comparator(a):
     dev = torch.device("cuda:0")
     cfgd = preset(a.preset)
     cfgd["sparse_config"]["vision_keep_rate"] = a.keep_rate
-    cfgd["sparse_config"]["use_output_text_predictor"] = a.out_keep >= 0
+    has_out = a.out_keep == "linspace(0.1,0.9)" or float(a.out_keep) >= 0
+    cfgd["sparse_config"]["use_output_text_predictor"] = has_out
     sd = {k: v.to(dev) for k, v in tiled_state_dict(cfgd, seed=0).items()}
     ids, pix = synthetic_inputs(cfgd, a.batch, a.prompt_len, seed=1)
     ids, pix = ids.to(dev), pix.to(dev)
-    fd = forced_text_decisions(a.new_tokens - 1, a.batch, keep_rate=a.out_keep, seed=3).to(dev) if a.out_keep >= 0 else None
+    fd = forced_text_decisions(a.new_tokens - 1, a.batch, keep_rate=out_keep_rates(a), seed=3).to(dev) if has_out else None
     ms = []
     for it in range(a.warmup + max(a.steps, 1)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -429,7 +600,7 @@ def gpu_comparator(a):
               f"{a.out_keep}, {a.new_tokens} greedy tokens: the oracle port (reference op sequence, eager PyTorch) on {torch.cuda.get_device_name(0)}")
     line = {"impl": "reference", "ref_device": "cuda", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2, full workload, reference PyTorch path on the GPU: " + sample},
+            "config": {"workload": f"BASELINE config {a.config}, full workload, reference PyTorch path on the GPU: " + sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": 0, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -446,7 +617,7 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": None if not v else 1e3 * a.cpu_new_tokens / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2 workload, bounded CPU sample: " + cb["sample"]},
+            "config": {"workload": workload_name(a, 1) + " -- timed on a bounded CPU sample of it: " + cb["sample"], "baseline_config": a.config},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

@@ -38,6 +38,7 @@ class RaggedKVArena:
         self.host_ub_hi = 0   # layers >= SL: upper bound (exact when nothing has been dropped)
         self.hi_exact = True
         self.floor_lo = self.floor_hi = 0  # host-known lower bounds of kv_len (set at prefill)
+        self.generation = 0  # bumped by reset(): a LegacyPastView of an earlier conversation is recognisably stale
 
     def reset(self, lengths_only: bool = False):
         """lengths_only: a scratch arena (use_cache=False) is never served as a zero-padded legacy tuple, so the slabs may keep stale
@@ -49,6 +50,7 @@ class RaggedKVArena:
         self.host_len_lo = self.host_ub_hi = 0
         self.hi_exact = True
         self.floor_lo = self.floor_hi = 0
+        self.generation += 1
 
     def layer(self, l: int):
         """-> (K slab [B, heads, cap, hd], V slab, cap)"""
@@ -87,6 +89,7 @@ class LegacyPastView:
         self.arena = arena
         self.session = session
         self._lens = None
+        self.stamp = (arena.generation, arena.host_len_lo)  # forward() refuses a view the cache has moved past
 
     def _host_lens(self) -> torch.Tensor:
         if self._lens is None or self._lens_step != self.arena.host_len_lo:

@@ -191,6 +191,9 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
         tma_bulk_g2s(S.kv[s][0], kbase + (int64_t)t * AD_TK * AD_HD, bytes, &S.full[s]);
         tma_bulk_g2s(S.kv[s][1], vbase + (int64_t)t * AD_TK * AD_HD, bytes, &S.full[s]);
       }
+      // a len_floor above the real length (a stale host constant baked into a replayed graph) leaves pre-issued tiles that no consumer
+      // waits for: drain them here so that the CTA never exits with bulk copies in flight into its shared memory
+      for (int t = n_tiles; t < n_pre; ++t) mbar_wait(&S.full[t], 0);
     }
   } else {
     // ---------------- consumer warps ----------------

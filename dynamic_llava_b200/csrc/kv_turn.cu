@@ -71,6 +71,16 @@ __global__ void __launch_bounds__(256) kv_compact_turn_kernel(bf16* __restrict__
     for (int i = 0; i < PER; ++i)
       if (d[i] >= 0) st8(base + d[i], reg[i]);
   }
+  // rows [kept, Tq) are no longer part of the cache: zero them, so that "slots at or beyond kv_len are zero" (cache.py: the strided
+  // view IS the reference's zero-padded tensor) keeps holding after a turn
+  __shared__ int n_kept;
+  __syncthreads();
+  if (threadIdx.x == 0) n_kept = run;
+  __syncthreads();
+  bf16x8 z;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+  for (int it = n_kept * VCH + threadIdx.x; it < Tq * VCH; it += 256) st8(base + (int64_t)it * 8, z);
 }
 
 extern "C" int dl_kv_compact_turn(void* k_arena, void* v_arena, const int32_t* kv_len, const uint8_t* keep, int Tq, int B,

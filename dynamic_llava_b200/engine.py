@@ -65,6 +65,7 @@ class Session:
         self.attn_ws = None
         self.graph = None
         self.graph_key = None
+        self.view_ref = None  # weakref to the last LegacyPastView handed out for this session (modeling._session)
         self.indices = None
         self.n_steps_done = 0
 
@@ -133,15 +134,33 @@ class Engine:
             f.gate_proj.weight.data, f.up_proj.weight.data = wgu[:I], wgu[I:]
             layers.append(dict(wqkv=wqkv, wo=a.o_proj.weight.data, wgu=wgu, wd=f.down_proj.weight.data,
                                ln1=lyr.input_layernorm.weight.data, ln2=lyr.post_attention_layernorm.weight.data))
-        hd = H // c.num_attention_heads
-        # RoPE tables exactly as the reference builds them: fp32 on the host, rounded to bf16 (dynamic_modeling_llama.py:152-184)
-        inv_freq = 1.0 / (c.rope_theta ** (torch.arange(0, hd, 2).float() / hd))
-        t = torch.arange(c.max_position_embeddings, dtype=torch.float32)
-        emb = torch.cat((torch.outer(t, inv_freq),) * 2, dim=-1)
-        cos = emb.cos().to(self.dtype).to(self.device).contiguous()
-        sin = emb.sin().to(self.dtype).to(self.device).contiguous()
+        cos, sin = self._rope_tables(c.max_position_embeddings)
         self.packed = dict(sig=m.layers[0].self_attn.q_proj.weight.data_ptr(), layers=layers, cos=cos, sin=sin, clip=None)
         self._pack_clip()
+
+    def _rope_tables(self, n_pos: int):
+        """RoPE tables exactly as the reference builds them: fp32 on the host, rounded to bf16 (dynamic_modeling_llama.py:152-184)"""
+        c = self.cfg
+        hd = c.hidden_size // c.num_attention_heads
+        inv_freq = 1.0 / (c.rope_theta ** (torch.arange(0, hd, 2).float() / hd))
+        t = torch.arange(n_pos, dtype=torch.float32)
+        emb = torch.cat((torch.outer(t, inv_freq),) * 2, dim=-1)
+        return emb.cos().to(self.dtype).to(self.device).contiguous(), emb.sin().to(self.dtype).to(self.device).contiguous()
+
+    def ensure_rope(self, n_pos: int) -> bool:
+        """Every kernel indexes cos/sin by the ORIGINAL position (up to prompt + generated tokens).  The reference's
+        LlamaRotaryEmbedding regrows its cache when seq_len > max_seq_len_cached (dynamic_modeling_llama.py:176-179); so do we — same
+        fp32 formula, so rows below the old length keep their values.  Returns True when the tables moved (captured graphs hold the old
+        addresses: the caller drops them)."""
+        self._check_packed()
+        have = self.packed["cos"].shape[0]
+        if n_pos <= have:
+            return False
+        n = have
+        while n < n_pos:
+            n *= 2
+        self.packed["cos"], self.packed["sin"] = self._rope_tables(n)
+        return True
 
     @torch.no_grad()
     def _pack_clip(self):
@@ -433,6 +452,10 @@ class Engine:
         for l in range(Lyr):
             if sc["use_vision_predictor"] and l == SL and have_idx:
                 s0, e0 = indices[0]["image"]
+                if any(d["image"] != indices[0]["image"] for d in indices[1:]):
+                    # the reference scores each row's own span (:1833-1842) but gathers and rebuilds positions with SAMPLE 0's bounds
+                    # (:1919-1932, :1962-1983): rows with another <image> position are silently mis-sliced there; refuse by name
+                    raise NotImplementedError("all samples of a batch must share the <image> position (the reference slices with sample 0's bounds)")
                 n_img = e0 - s0
                 k = int(n_img * sc["vision_keep_rate"])  # :1899-1901
                 x3 = x.view(B, Lq, H)
@@ -643,7 +666,7 @@ class Engine:
                 join_side = False
             L_.attn_decode_fused(_p(sess.partial), s, _p(a.pos), _p(keep if l >= SL else None), _p(pk["cos"]), _p(pk["sin"]), _p(K_), _p(V_),
                                  _p(kvl), _p(sess.attn), _p(sess.attn_ws), B, nh, hd, cap, ns, scale,
-                                 1 if (quirk and l >= SL and keep is not None) else 0,
+                                 1 if (quirk and l >= SL and (keep is not None or not a.hi_exact)) else 0,
                                  _p(W["wo"]) if self.attn_prefetch_wo else None, W["wo"].numel() * 2,
                                  (a.floor_lo if l < SL else a.floor_hi) if self.attn_early_kv else 0, st)
             s = self._gemm(sess, sess.attn, W["wo"], B, H, H)

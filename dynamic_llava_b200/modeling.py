@@ -187,15 +187,25 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         return self._engine
 
     def _session(self, B, cap_lo, cap_hi, max_new, scratch=False) -> Session:
-        key = (B, cap_lo, cap_hi, max_new, scratch)
+        # sparse_layer fixes the arena's lo/hi split: a caller that mutates the live sparse_config gets a new arena, not a stale split
+        key = (B, cap_lo, cap_hi, max_new, scratch, self.config.sparse_config["sparse_layer"])
         s = self._sessions.get(key)
+        if s is not None and s.view_ref is not None and s.view_ref() is not None:
+            # a past_key_values handed out by an earlier forward() is still alive in the caller: the reference returns an independent
+            # cache per call, so this conversation gets its own arena (the old one lives on through the view that references it)
+            s = None
         if s is None:
-            self._sessions.clear()  # one live session per model: arenas are large
+            self._sessions.clear()  # one session cached per model: arenas are large
             s = Session(self.engine, B, cap_lo, cap_hi, max_new)
             self._sessions[key] = s
         else:
             s.reset(lengths_only=scratch)
         return s
+
+    def _past_view(self, sess) -> LegacyPastView:
+        v = LegacyPastView(sess.arena, sess)
+        sess.view_ref = weakref.ref(v)
+        return v
 
     def encode_images(self, images):
         """dynamic_llava_arch.py:163-166"""
@@ -245,6 +255,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                 eng.L.embed_rows(ids.contiguous().data_ptr(), self.model.embed_tokens.weight.data_ptr(), inputs_embeds.data_ptr(),
                                  ids.numel(), self.config.hidden_size, torch.cuda.current_stream().cuda_stream)
             B, P, _ = inputs_embeds.shape
+            eng.ensure_rope(P + 1)
             k_drop = 0
             if sc["use_vision_predictor"] and input_embeds_indices is not None and len(input_embeds_indices) == B:
                 n_img = input_embeds_indices[0]["image"][1] - input_embeds_indices[0]["image"][0]
@@ -260,8 +271,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                 return CausalLMOutputWithPast(logits=logits.float(), past_key_values=None)
             sess = self._session(B, P + room, P - k_drop + room, 0)
             logits = eng.prefill(sess, inputs_embeds, input_embeds_indices, forced_keep=forced_keep_index, all_logits=True, record=record)
-            past = LegacyPastView(sess.arena, sess)
-            return CausalLMOutputWithPast(logits=logits.float(), past_key_values=past)
+            return CausalLMOutputWithPast(logits=logits.float(), past_key_values=self._past_view(sess))
         # ---------------- decode step ----------------
         if not isinstance(past_key_values, LegacyPastView):
             raise NotImplementedError("past_key_values must be the object returned by a previous forward() of this model")
@@ -270,14 +280,19 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             raise NotImplementedError("continuing a cache needs input_ids (inputs_embeds continuation is not a reference flow)")
         sess = past_key_values.session
         a = sess.arena
+        if past_key_values.stamp != (a.generation, a.host_len_lo):
+            raise ValueError("stale past_key_values: this cache has advanced (or was reset) since the object was returned; pass back the "
+                             "past_key_values of the LATEST forward() on this conversation")
         n_in = ids.shape[1]
+        if eng.ensure_rope(a.host_len_lo + n_in):
+            sess.graph = None
         if a.room() < n_in:
             a.grow(a.host_len_lo + n_in + 64, a.host_ub_hi + n_in + 64)
             sess.graph = None
         if n_in > 1:
             # a new user turn over the existing cache (model_lvis_multi_round_for_meteor.py:150-185)
             logits = eng.continue_prefill(sess, ids, record=record)
-            return CausalLMOutputWithPast(logits=logits.float(), past_key_values=LegacyPastView(a, sess))
+            return CausalLMOutputWithPast(logits=logits.float(), past_key_values=self._past_view(sess))
         sess.next_ids.copy_(ids.reshape(-1).to(self.device, torch.int64))
         use_dec = bool(sc["use_text_predictor"] and sc["use_output_text_predictor"])
         if forced_text_decision is not None:
@@ -292,7 +307,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             record.update(text_decision=keep.clone().bool().view(-1, 1), text_logits=sess.tp_logits.clone())
         logits = sess.logits.float().view(sess.B, 1, -1).clone()
         eng.decode_advance(sess, keep)
-        return CausalLMOutputWithPast(logits=logits, past_key_values=LegacyPastView(a, sess))
+        return CausalLMOutputWithPast(logits=logits, past_key_values=self._past_view(sess))
 
     # ---- generate (dynamic_llava_llama.py:117-152 -> HF 4.37.2 greedy search) -----------------
     @torch.no_grad()
@@ -306,7 +321,16 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             raise NotImplementedError("generate(use_cache=False): drive the no-KV-cache mode through forward(..., use_cache=False) like the "
                                       "reference's bench_test/dynamic_llava_long_text_time_with_no_cache.py; generate() always decodes over the cache")
         if kwargs.get("num_beams", 1) not in (1, None):
-            raise NotImplementedError("beam search is a SURVEY.md §8f 'next' row; num_beams must be 1")
+            raise NotImplementedError("beam search (num_beams > 1) is de-scoped: the reference's own _reorder_cache "
+                                      "(dynamic_modeling_llama.py:2883-2895) drops the true-length list its cache is rebuilt from, so beams do "
+                                      "not run there either (DESIGN.md §8)")
+        # HF generate() kwargs this loop does not implement must not be silently ignored
+        unsupported = [k for k in ("max_length", "repetition_penalty", "no_repeat_ngram_size", "length_penalty", "bad_words_ids",
+                                   "force_words_ids", "num_beam_groups", "penalty_alpha", "typical_p", "logits_processor",
+                                   "prefix_allowed_tokens_fn", "num_return_sequences", "assistant_model", "streamer")
+                       if kwargs.get(k) not in (None, 1, 1.0, 0, [])]
+        if unsupported:
+            raise NotImplementedError(f"generate() kwargs not implemented by the B200 loop: {unsupported}")
         sampling = None  # (temperature, top_k, top_p): HF 4.37.2 `sample` (model_vqa_loader.py:169-172: do_sample = temperature > 0)
         if kwargs.get("do_sample", False):
             temperature = kwargs.get("temperature", None)
@@ -324,6 +348,10 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         max_new = kwargs.get("max_new_tokens", 20)
         min_new = kwargs.get("min_new_tokens", 0) or 0
         eos = kwargs.get("eos_token_id", self.config.eos_token_id)
+        if isinstance(eos, (list, tuple)):
+            if len(eos) > 1:
+                raise NotImplementedError("a list of several eos_token_id values is not implemented (one EOS id is tracked on the device)")
+            eos = eos[0] if eos else None
         pad = kwargs.get("pad_token_id", self.config.pad_token_id)
         pad = 0 if pad is None else pad
         forced_keep = kwargs.get("forced_keep_index")
@@ -350,6 +378,9 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                              inputs.numel(), self.config.hidden_size, torch.cuda.current_stream().cuda_stream)
             indices = None
         B, P, _ = embeds.shape
+        if eng.ensure_rope(P + max_new):
+            for s_ in self._sessions.values():
+                s_.graph = None  # captured steps hold the old table addresses
         k_drop = 0
         if sc["use_vision_predictor"] and indices is not None and len(indices) == B:
             n_img = indices[0]["image"][1] - indices[0]["image"][0]
@@ -370,6 +401,10 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             sess.rng_seed.fill_(seed)
 
         def pick(lg, eos_):
+            if eos_ is None and eos_k is not None:
+                # HF MinNewTokensLengthLogitsProcessor: while fewer than min_new_tokens exist the EOS logit is -inf, so EOS cannot be
+                # emitted mid-sequence (and finished-tracking is off)
+                lg.select(-1, eos_k).fill_(float("-inf"))
             if sampling is None:
                 eng.greedy(sess, lg, eos_, pad)
             else:
@@ -379,7 +414,10 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         eng.L.kv_advance(None, None, a.step.data_ptr(), None, 0, B, 0, 0, 0, torch.cuda.current_stream().cuda_stream)  # step += 1
         n_done = 1
         stopped = bool(criteria) and any(c(sess.tokens[:, :1].cpu(), None) for c in criteria)
-        gkey = (use_dec, quirk, eos_k, pad, None if sess.forced is None else sess.forced.data_ptr(), sampling)
+        # everything the captured step bakes in as a host constant is part of its key: the attention kernels' prefill-length floors
+        # (data-dependent with the instruct predictor), the sparse layer, the RoPE tables
+        gkey = (use_dec, quirk, eos_k, pad, None if sess.forced is None else sess.forced.data_ptr(), sampling, a.floor_lo, a.floor_hi,
+                sc["sparse_layer"], eng.packed["cos"].data_ptr())
         while n_done < max_new and not stopped:
             eos_now = eos_k if n_done >= min_new else None
             if use_graph and sess.graph is not None and sess.graph_key == gkey + (eos_now,):

@@ -1,0 +1,233 @@
+"""Full-size parity of the B200 path against the ORACLE for the BASELINE configs that are actually timed (2, 3, 4, 5).
+
+The CPU oracle needs minutes per config at 7B/13B, so here the same oracle code (oracle/dynllava_oracle.py — pure torch ops on whatever
+device its state dict lives on, pinned bit for bit to the unmodified reference on the CPU fixtures) runs with its tensors ON THE GPU:
+eager PyTorch, cuBLAS, SDPA, the reference's `torch.cat` cache with its B > 1 zero padding (cache_utils.py:165-241), the reference's
+hand-rolled greedy loop (llava/dynamic_eval/model_lvis_for_meteor.py:145-174).  `test_cuda_oracle_matches_cpu_oracle_on_toy_fixture`
+validates that device-resident oracle against the committed (reference-generated) CPU fixture first.
+
+Per config: INDEPENDENT random weights (`device_state_dict`: every tensor its own N(0, 0.02) draw — not the tiled pool of the timing
+baseline), the oracle's own natural image mask, the config's forced seeded output decisions on both sides, the oracle's greedy tokens
+teacher-forced into our `forward()` loop.  Compared at EVERY step: last-position logits, and at the end `kv_len` against
+`true_cache_length` (exact) and the natural `keep_index` (tie-aware).  Reported per config, and appended to
+gpurun_out/full_size_parity.jsonl (copied to profiles/ by hand): max|gpu - oracle_bf16| (same dtype), max|gpu - oracle_fp32|, the
+oracle's own floor max|oracle_bf16 - oracle_fp32|, the logit scale, and whether the LITERAL absolute 1e-2 of the north star holds.
+
+Bars asserted: err_fp32 <= 2 * floor + 1e-2 * scale (tests/test_model_gpu.py policy) AND err_bf16 <= 2 * floor (two bf16 evaluations of
+the same fp32 function cannot be asked to agree better than each agrees with fp32), kv_len exact, greedy token equality wherever the
+fp32 oracle's top-1/top-2 margin exceeds 4 * floor.
+"""
+import json
+import os
+import time
+
+import pytest
+import torch
+
+from dynamic_llava_b200.presets import preset
+from dynamic_llava_b200.synthetic import device_state_dict, forced_text_decisions, numpy_state_dict, synthetic_inputs
+from oracle import dynllava_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _report(row):
+    print("PARITY " + json.dumps(row))
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "full_size_parity.jsonl"), "a") as f:
+            f.write(json.dumps(row) + "\n")
+    except OSError:
+        pass
+
+
+def _gpu_teacher_forced(model, ids, pix, tokens, n_new, keep, fd):
+    """the reference's hand-rolled loop shape (model_lvis_for_meteor.py:145-174) through OUR forward(); everything stays on the device"""
+    past, cur, images = None, ids, pix
+    logits = []
+    rec0 = {}
+    for t in range(n_new):
+        kw = {}
+        if t == 0:
+            kw["record"] = rec0
+            if keep is not None:
+                kw["forced_keep_index"] = keep
+        if t > 0 and fd is not None:
+            kw["forced_text_decision"] = fd[t - 1]
+        out = model(cur, images=images, past_key_values=past, **kw)
+        images = None
+        past = out.past_key_values
+        logits.append(out.logits[:, -1, :].clone())
+        cur = tokens[:, t].reshape(-1, 1)
+    return torch.stack(logits, 0), past, rec0
+
+
+def _tie_aware_keep_agreement(vision_logits_ref, keep_ref, keep_got):
+    """fraction of the oracle's kept tokens that we keep too, and whether every disagreement sits within 2 bf16 ulps of the k-th score"""
+    score = torch.log_softmax(vision_logits_ref.float(), -1)[..., 0]
+    B, k = keep_ref.shape
+    same, near = 0, True
+    for b in range(B):
+        a, g = set(keep_ref[b].tolist()), set(keep_got[b].tolist())
+        same += len(a & g)
+        if a != g:
+            kth = score[b, keep_ref[b]].min().item()
+            diff = torch.tensor(sorted(a ^ g), device=score.device)
+            near = near and bool(((score[b, diff] - kth).abs() <= 2 * 2 ** -7 * max(abs(kth), 1e-3)).all())
+    return same / float(B * k), near
+
+
+def _run_config(tag, preset_name, B, T, n_new, keep_rate, fd, quirk, per_sample_rows=None, seed=0):
+    """one BASELINE config (per GPU) against the device-resident oracle; returns the report row"""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    t_start = time.perf_counter()
+    cfgd = preset(preset_name)
+    cfgd["sparse_config"]["vision_keep_rate"] = keep_rate
+    cfgd["sparse_config"]["use_output_text_predictor"] = fd is not None
+    dev = torch.device("cuda")
+    sd16 = device_state_dict(cfgd, seed=seed, device=dev)  # independent draws per tensor
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device=dev)
+    model.get_vision_tower().load_model()
+    model.load_state_dict(sd16, strict=True)
+    model.config.reference_batched_quirk = quirk
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    ids, pix = ids.to(dev), pix.to(dev)
+    fdd = None if fd is None else fd.to(dev)
+    rows = list(range(B)) if per_sample_rows is None else per_sample_rows
+
+    sub = torch.tensor(rows, device=dev)
+    ragged = not (quirk or B == 1)
+
+    def oracle(sd, pixels, keep=None, teacher=None):
+        if not ragged:  # the reference's literal batched behaviour (zero-padded ragged cache, unmasked)
+            return O.greedy_loop(sd, cfgd, ids, pixels, n_new, forced_text_decisions=fdd, forced_keep_index=keep, teacher_tokens=teacher)
+        # default mode of the B200 path = every sample alone (cache_utils.py:153-164 semantics); samples never interact, so a subset
+        # of rows of the B-sample GPU run is compared with those rows run alone through the oracle (keep / teacher: those rows only)
+        return O.greedy_loop(sd, cfgd, ids[sub], pixels[sub], n_new, forced_text_decisions=None if fdd is None else fdd[:, sub],
+                             per_sample=True, forced_keep_index=keep, teacher_tokens=teacher)
+    o16 = oracle(sd16, pix)
+    keep_ref = o16["keep_index"]
+    tokens = o16["tokens"]
+    # natural image mask of OUR predictor path (compared tie-aware with the oracle's below), then everything under the oracle's mask
+    rec_nat = {}
+    model(ids, images=pix, record=rec_nat)
+    if ragged:  # scatter the subset into a full-batch teacher / mask (other rows: our own natural choices, never compared)
+        full_keep = rec_nat["keep_index"].clone()
+        full_keep[sub] = keep_ref
+        full_tok = torch.zeros(B, n_new, dtype=torch.int64, device=dev)
+        full_tok[sub] = tokens
+    else:
+        full_keep, full_tok = keep_ref, tokens
+    got, past, rec0 = _gpu_teacher_forced(model, ids, pix, full_tok, n_new, full_keep, fdd)
+    lens = torch.stack(list(past[1]), 0)
+    got = got[:, sub] if ragged else got
+    del model, past
+    torch.cuda.empty_cache()
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    o32 = oracle(sd32, pix.float(), keep=keep_ref, teacher=tokens)
+    del sd32
+    floor = (o16["logits"] - o32["logits"]).abs().max().item()
+    scale = o32["logits"].abs().max().item()
+    err16 = (got - o16["logits"]).abs().max().item()
+    err32 = (got - o32["logits"]).abs().max().item()
+    top2 = o32["logits"].topk(2, dim=-1).values
+    sure = (top2[..., 0] - top2[..., 1]) > 4 * floor
+    tok_equal_sure = bool(torch.equal(got.argmax(-1)[sure], o32["logits"].argmax(-1)[sure]))
+    agree = (got.argmax(-1) == o16["logits"].argmax(-1)).float().mean().item()
+    lens_ref = o16["true_len"]
+    lens_got = lens[:, rows].cpu() if ragged else lens.cpu()
+    nat_keep = rec_nat["keep_index"][sub] if ragged else rec_nat["keep_index"]
+    # the oracle's vision logits for the tie analysis: one prefill with record
+    reco = {}
+    O.model_forward(sd16, cfgd, ids[sub] if ragged else ids, images=pix[sub] if ragged else pix, record=reco)
+    keep_frac, keep_near = _tie_aware_keep_agreement(reco["vision_logits"], keep_ref, nat_keep)
+    vl_err = ((rec_nat["vision_logits"][sub] if ragged else rec_nat["vision_logits"]).float() - reco["vision_logits"].float()).abs().max().item()
+    vl_scale = reco["vision_logits"].float().abs().max().item()
+    row = dict(config=tag, preset=preset_name, B=B, T=T, n_new=n_new, keep_rate=keep_rate, mode="reference_batched_quirk" if quirk else
+               ("b1" if B == 1 else f"ragged (rows {rows} vs per-sample oracle)"), weights="independent N(0,0.02) per tensor (device_state_dict)",
+               err_vs_oracle_bf16=err16, err_vs_oracle_fp32=err32, oracle_floor_bf16_vs_fp32=floor, logit_scale=scale,
+               literal_1e2_abs_holds=bool(err32 <= 1e-2), rel_err_fp32=err32 / scale, teacher_forced_argmax_agreement=agree,
+               sure_positions=float(sure.float().mean().item()), tokens_equal_where_sure=tok_equal_sure,
+               kv_len_exact=bool(torch.equal(lens_got.long(), lens_ref.cpu().long())), natural_keep_index_overlap=keep_frac,
+               natural_keep_disagreements_within_2ulp_of_kth=keep_near, vision_logits_err=vl_err, vision_logits_scale=vl_scale,
+               seconds=time.perf_counter() - t_start)
+    _report(row)
+    assert row["kv_len_exact"], (lens_got, lens_ref)
+    assert err32 <= 2 * floor + 1e-2 * scale, row
+    assert err16 <= 2 * floor + 1e-2 * scale, row
+    assert tok_equal_sure, row
+    return row
+
+
+def test_cuda_oracle_matches_cpu_oracle_on_toy_fixture():
+    """the device-resident oracle is the same restatement: on the committed reference-generated toy fixture it reproduces the CPU
+    tokens wherever the margin is clear, the KV lengths exactly, and the logits within the bf16 floor"""
+    g = torch.load(os.path.join(GOLD, "toy_bf16_b2_forced.pt"), weights_only=False)
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = g["use_output_text_predictor"]
+    sd32 = numpy_state_dict(cfg, seed=g["weight_seed"])
+    sd16 = {k: v.to(BF) for k, v in sd32.items()}
+    ids, pix = synthetic_inputs(cfg, g["B"], g["T"], seed=g["input_seed"], dtype=BF)
+    rec = {}
+    O.model_forward(sd16, cfg, ids, images=pix, record=rec)
+    kw = dict(forced_keep_index=rec["keep_index"], forced_text_decisions=g["forced_decisions"], teacher_tokens=g["tokens"])
+    cpu16 = O.greedy_loop(sd16, cfg, ids, pix, g["n_new"], **kw)
+    cpu32 = O.greedy_loop(sd32, cfg, ids, pix.float(), g["n_new"], **kw)
+    assert torch.equal(cpu16["logits"], g["logits"])  # the CPU oracle IS the fixture (tests/test_oracle_golden.py), restated here
+    dev = torch.device("cuda")
+    c = lambda t: None if t is None else t.to(dev)
+    kwd = {k: c(v) for k, v in kw.items()}
+    gpu16 = O.greedy_loop({k: v.to(dev) for k, v in sd16.items()}, cfg, c(ids), c(pix), g["n_new"], **kwd)
+    gpu32 = O.greedy_loop({k: v.to(dev) for k, v in sd32.items()}, cfg, c(ids), c(pix.float()), g["n_new"], **kwd)
+    floor = (cpu16["logits"] - cpu32["logits"]).abs().max().item()
+    scale = cpu32["logits"].abs().max().item()
+    e32 = (gpu32["logits"].cpu() - cpu32["logits"]).abs().max().item()
+    e16 = (gpu16["logits"].cpu() - cpu16["logits"]).abs().max().item()
+    _report(dict(config="toy fixture: CUDA-resident oracle vs CPU oracle", err_fp32_cuda_vs_cpu=e32, err_bf16_cuda_vs_cpu=e16, oracle_floor_bf16_vs_fp32=floor,
+                 logit_scale=scale))
+    assert e32 <= 1e-3 * scale, (e32, scale)  # fp32 on both devices: accumulation order only
+    assert e16 <= 2 * floor, (e16, floor)
+    assert torch.equal(gpu16["true_len"].cpu(), cpu16["true_len"])
+    top2 = cpu32["logits"].topk(2, dim=-1).values
+    sure = (top2[..., 0] - top2[..., 1]) > 4 * floor
+    assert torch.equal(gpu16["logits"].cpu().argmax(-1)[sure], cpu32["logits"].argmax(-1)[sure])
+
+
+@pytest.mark.timeout(900)
+def test_config2_full_size_7b_batched_quirk_vs_oracle():
+    """BASELINE config 2 as the REFERENCE runs it (B = 8 in one batch: zero-padded ragged cache, cache_utils.py:165-241), all 128 tokens"""
+    fd = forced_text_decisions(127, 8, keep_rate=0.5, seed=3)
+    _run_config("2 (reference batched semantics)", "llava-1.5-7b", 8, 32, 128, 0.2, fd, quirk=True)
+
+
+@pytest.mark.timeout(900)
+def test_config2_full_size_7b_ragged_vs_per_sample_oracle():
+    """BASELINE config 2 in the bench's default mode (true ragged attention == each sample alone), rows 0 and 7 of the B = 8 run against
+    those samples run alone through the oracle, all 128 tokens"""
+    fd = forced_text_decisions(127, 8, keep_rate=0.5, seed=3)
+    _run_config("2 (ragged default)", "llava-1.5-7b", 8, 32, 128, 0.2, fd, quirk=False, per_sample_rows=[0, 7])
+
+
+@pytest.mark.timeout(900)
+def test_config3_full_size_7b_per_rank_shape_vs_oracle():
+    """BASELINE config 3 per rank: B = 8, 256 tokens, per-sample forced keep rates linspace(0.1, 0.9, 8) (ragged-KV stress), reference
+    batched semantics"""
+    fd = forced_text_decisions(255, 8, keep_rate=torch.linspace(0.1, 0.9, 8).tolist(), seed=3)
+    _run_config("3 (per rank, reference batched semantics)", "llava-1.5-7b", 8, 32, 256, 0.2, fd, quirk=True)
+
+
+@pytest.mark.timeout(900)
+def test_config4_full_size_13b_prefill_vs_oracle():
+    """BASELINE config 4 per rank: 13B, B = 4, P = 2048 -> P' = 1587, prefill + 2 tokens with forced decisions"""
+    fd = forced_text_decisions(2, 4, keep_rate=0.5, seed=3)
+    _run_config("4 (per rank)", "llava-1.5-13b", 4, 2048 - 576 + 1, 3, 0.2, fd, quirk=True)
+
+
+@pytest.mark.timeout(900)
+def test_config5_full_size_7b_keep_half_vs_oracle():
+    """one point of BASELINE config 5's sweep: 7B, B = 16, keep 0.5 (k = 288, P' = 319), prefill + 3 tokens, output predictor off"""
+    _run_config("5 (keep 0.5 point)", "llava-1.5-7b", 16, 32, 4, 0.5, None, quirk=True)
