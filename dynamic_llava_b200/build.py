@@ -27,7 +27,7 @@ SOURCES = [
     "attn_prefill_tc2.cu",
     "attn_prefill_tc4.cu",
     "skinny_gemm.cu",
-    "gemm_tc.cu",
+    "gemm2.cu",
     "decode_fused.cu",
     "predictor_ops.cu",
     "sample.cu",

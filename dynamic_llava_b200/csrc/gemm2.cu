@@ -1,0 +1,366 @@
+// Dense bf16 GEMM for every nn.Linear at q_len > 1 (prefill q/k/v/o/gate/up/down, CLIP, predictor blocks, projector, lm_head over
+// all positions):      out[M, N] = epilogue( X[M, K] . W[N, K]^T )        (nn.Linear layout, fp32 accumulate)
+// Reference call sites: llava/model/language_model/dynamic_modeling_llama.py:294-330 (LlamaMLP), :377-392 + :1011-1013 + :1127
+// (q/k/v/o_proj), :1324-1346 (VisionPredictor linears), :2709 (lm_head); custom_transformer_layer.py:86-180 (predictor blocks);
+// multimodal_projector/builder.py:172-179; HF CLIPEncoderLayer / CLIPVisionEmbeddings (unvendored).
+//
+// B200 design: persistent kernel, one CTA per SM, CTAs paired into 2-CTA clusters that share one 256 x BN output tile
+// (`tcgen05.mma.cta_group::2`, M = 256, N = BN in {256, 128}).  Per pair and 64-wide k-block: each CTA TMA-loads ITS 128 rows of X and
+// ITS BN/2 rows of W (so every operand byte is fetched from L2 once per pair and each SM's tensor core reads only half of B from its
+// own shared memory); the leader CTA's single elected thread issues the MMAs for both SMs; accumulators live in TMEM, double
+// buffered (2 x BN columns), so the four epilogue warps of each CTA drain tile i (tcgen05.ld -> bias / activation / residual /
+// SwiGLU -> bf16 -> swizzled smem -> TMA store) while the tensor cores already run tile i+1.
+//   warp 0: TMA producer (6- or 8-stage mbarrier ring, both CTAs; completion bytes of BOTH CTAs land on the leader's `full` barrier)
+//   warp 1: MMA issuer (leader CTA only) + TMEM allocation (both CTAs, cta_group::2)
+//   warps 2-5: epilogue (TMEM lane quarter = warp % 4)
+// Barriers: full[s] (leader: 1 arrival + 2 x stage bytes), empty[s] (both CTAs, multicast tcgen05.commit), tmem_full[a] (both CTAs,
+// multicast commit), tmem_empty[a] (leader: 8 arrivals = 2 CTAs x 4 epilogue warps, the peer's arrive remotely through DSMEM).
+// Tiles are dealt round-robin to the pairs in bands of 8 m-tiles (m fastest inside a band) so that the pairs running concurrently
+// share W panels and an L2-sized band of X.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/dynllava_b200.h"
+
+#define G2_BK 64
+#define G2_THREADS 192
+
+enum { G2_EPI_NONE = 0, G2_EPI_GELU = 1, G2_EPI_QUICK_GELU = 2, G2_EPI_RESIDUAL = 3, G2_EPI_SWIGLU = 4 };
+
+template <int BN>
+struct G2Smem {
+  static constexpr int STAGES = BN == 256 ? 6 : 8;
+  alignas(1024) bf16 a[STAGES][128 * G2_BK];
+  alignas(1024) bf16 b[STAGES][(BN / 2) * G2_BK];
+  alignas(1024) uint8_t stage_out[4][2][4096];  // per epilogue warp: two 32-row x 64-column bf16 boxes (128B swizzle)
+  alignas(8) uint64_t full[STAGES];
+  alignas(8) uint64_t empty[STAGES];
+  alignas(8) uint64_t tmem_full[2];
+  alignas(8) uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+DL_DEVINL uint32_t g2_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+DL_DEVINL void g2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in the CTA of rank `rank`
+DL_DEVINL uint32_t g2_mapa(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+DL_DEVINL void g2_mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-SM TMA load: data lands in THIS CTA's shared memory, the completion bytes on the barrier at `mbar_cluster_addr` (the leader's)
+DL_DEVINL void g2_tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint32_t mbar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+DL_DEVINL void g2_umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive (once complete) on the barrier at this offset in BOTH CTAs of the pair
+DL_DEVINL void g2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <int COLS>
+DL_DEVINL void g2_tmem_alloc(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+DL_DEVINL void g2_tmem_dealloc(uint32_t tmem_addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_addr), "n"(COLS) : "memory");
+}
+DL_DEVINL void g2_tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// tile -> (m-tile, n-tile): bands of 8 m-tiles, m fastest inside a band
+DL_DEVINL void g2_tile_coords(int tile, int tiles_m, int tiles_n, int& mt, int& nt) {
+  const int band_sz = 8 * tiles_n;
+  const int band = tile / band_sz, r = tile - band * band_sz;
+  const int m_in_band = min(8, tiles_m - band * 8);
+  nt = r / m_in_band;
+  mt = band * 8 + (r - nt * m_in_band);
+}
+
+DL_DEVINL float g2_gelu_erf(float y) { return 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f)); }
+
+// EPI_SWIGLU: W = [gate rows (I) | up rows (I)]; the pair's B tile is gate rows [128 nt, +128) (CTA 0) and the matching up rows
+// (CTA 1), so accumulator columns [0,128) / [128,256) hold gate / up of the SAME 128 outputs; out is [M, I], N_out = I.
+template <int BN, int EPI>
+__global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                              const __grid_constant__ CUtensorMap tmap_w,
+                                                              const __grid_constant__ CUtensorMap tmap_o,
+                                                              const bf16* __restrict__ bias, const bf16* residual, int M, int N_out,
+                                                              int KB, int tiles_m, int tiles_n, int up_row0) {
+  using Smem = G2Smem<BN>;
+  constexpr int STAGES = Smem::STAGES;
+  constexpr int TM_COLS = 2 * BN;
+  constexpr uint32_t STAGE_BYTES = (128 + BN / 2) * G2_BK * 2;
+  constexpr int OUT_W = EPI == G2_EPI_SWIGLU ? BN / 2 : BN;  // output columns per tile
+  extern __shared__ uint8_t smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = g2_cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_tiles = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_o);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&S.tmem_full[a], 1);
+      mbar_init(&S.tmem_empty[a], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) g2_tmem_alloc<TM_COLS>(&S.tmem_base);
+  tc_fence_before();
+  g2_cluster_sync();  // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote arrive / 2-SM MMA
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs) ------------------------------------------------
+    if (elect_one()) {
+      pdl_launch_dependents();
+      pdl_wait();  // X (and a residual) come from the predecessor kernel
+      int it = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        int mt, nt;
+        g2_tile_coords(tile, tiles_m, tiles_n, mt, nt);
+        const int m0 = mt * 256 + (int)rank * 128;
+        const int n0 = EPI == G2_EPI_SWIGLU ? (rank == 0 ? nt * (BN / 2) : up_row0 + nt * (BN / 2)) : nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&S.empty[s], ph ^ 1);
+          const uint32_t full_leader = g2_mapa(smem_u32(&S.full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&S.full[s], 2 * STAGE_BYTES);
+          g2_tma_load_2d(S.a[s], &tmap_x, kb * G2_BK, m0, full_leader);
+          g2_tma_load_2d(S.b[s], &tmap_w, kb * G2_BK, n0, full_leader);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA) ------------------------------------------------
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(256, BN);
+      int it = 0, tc = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tc) {
+        const int a = tc & 1;
+        mbar_wait(&S.tmem_empty[a], ((tc >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&S.full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(S.a[s]));
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(S.b[s]));
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k) g2_umma(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          g2_commit_both(&S.empty[s]);  // the stage is free in both CTAs once these MMAs have read it
+        }
+        g2_commit_both(&S.tmem_full[a]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (both CTAs) ------------------------------------------------
+    const int q = warp & 3;  // TMEM lane quarter of this warp = rows [32q, 32q+32) of this CTA's half tile
+    uint8_t* stage0 = S.stage_out[q][0];
+    int tc = 0, nbox = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tc) {
+      int mt, nt;
+      g2_tile_coords(tile, tiles_m, tiles_n, mt, nt);
+      const int a = tc & 1;
+      const int row0 = mt * 256 + (int)rank * 128 + q * 32;
+      const int row = row0 + lane;
+      const int col_t = nt * OUT_W;
+      mbar_wait(&S.tmem_full[a], (tc >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+#pragma unroll 1
+      for (int c = 0; c < OUT_W / 64; ++c) {
+        uint32_t r[64];
+        uint32_t ru[EPI == G2_EPI_SWIGLU ? 64 : 1];
+        tmem_ld_32x32b_x32(tacc + c * 64, r);
+        tmem_ld_32x32b_x32(tacc + c * 64 + 32, r + 32);
+        if constexpr (EPI == G2_EPI_SWIGLU) {
+          tmem_ld_32x32b_x32(tacc + BN / 2 + c * 64, ru);
+          tmem_ld_32x32b_x32(tacc + BN / 2 + c * 64 + 32, ru + 32);
+        }
+        tmem_ld_wait();
+        if (c == OUT_W / 64 - 1) {  // this warp has read its whole accumulator slice: hand the TMEM stage back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) g2_mbar_arrive_cluster(g2_mapa(smem_u32(&S.tmem_empty[a]), 0));
+        }
+        const int col0 = col_t + c * 64;
+        bf16x8 pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = col0 + j * 8;
+          float f[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(r[j * 8 + u]);
+          if (bias != nullptr && col < N_out) {  // N_out % 8 == 0
+            float bv[8];
+            unpack8(ld8(bias + col), bv);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] += bv[u];
+          }
+          if constexpr (EPI == G2_EPI_GELU) {  // nn.GELU (erf) on the bf16-rounded linear output, as the reference's separate modules do
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] = g2_gelu_erf(rbf(f[u]));
+          } else if constexpr (EPI == G2_EPI_QUICK_GELU) {  // HF quick_gelu on bf16 tensors: t = bf16(1.702 y); s = bf16(sigmoid t); y * s
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float y = rbf(f[u]);
+              const float t = rbf(1.702f * y);
+              const float sg = rbf(1.0f / (1.0f + expf(-t)));
+              f[u] = y * sg;
+            }
+          } else if constexpr (EPI == G2_EPI_RESIDUAL) {  // x + linear(...): bf16 linear output, then a bf16 add (:1289, :1295)
+            if (row < M && col < N_out) {
+              float rv[8];
+              unpack8(ld8(residual + (int64_t)row * N_out + col), rv);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) f[u] = rbf(f[u]) + rv[u];
+            }
+          } else if constexpr (EPI == G2_EPI_SWIGLU) {  // bf16(bf16(silu(bf16 g)) * bf16 u)  (:328)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float g = rbf(f[u]), up = rbf(__uint_as_float(ru[j * 8 + u]));
+              f[u] = rbf(g / (1.0f + expf(-g))) * up;
+            }
+          }
+          pk[j] = pack8(f);
+        }
+        uint8_t* stage = stage0 + (nbox & 1) * 4096;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store that last used THIS box has read it
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<bf16x8*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk[j];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row0 < M && col0 < N_out) {  // the tensor map clips rows >= M and columns >= N_out
+          g2_tma_store_2d(&tmap_o, stage, col0, row0);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // (possibly empty) group: keeps the 2-deep accounting uniform
+        ++nbox;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  g2_cluster_sync();  // neither CTA frees TMEM (or exits) while the pair's MMAs / remote arrives may still touch it
+  if (warp == 1) g2_tmem_dealloc<TM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int g2_launch(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N_w, int N_out, int K,
+                     int up_row0, cudaStream_t stream) {
+  alignas(64) CUtensorMap tx, tw, to;
+  int rc = dl_make_tmap_2d(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, G2_BK);
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&tw, w, (uint64_t)N_w, (uint64_t)K, (uint64_t)K, BN / 2, G2_BK);
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&to, out, (uint64_t)M, (uint64_t)N_out, (uint64_t)N_out, 32, 64);
+  if (rc) return rc;
+  const int smem = (int)sizeof(G2Smem<BN>) + 1024;
+  static bool attr_set = false;
+  static int n_sm = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return dl_set_error((int)e, "dl_linear(smem attr)");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  constexpr int OUT_W = EPI == G2_EPI_SWIGLU ? BN / 2 : BN;
+  const int tiles_m = (M + 255) / 256, tiles_n = (N_out + OUT_W - 1) / OUT_W;
+  int n_pairs = n_sm / 2;
+  if (n_pairs > tiles_m * tiles_n) n_pairs = tiles_m * tiles_n;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * n_pairs);
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, EPI>, tx, tw, to, (const bf16*)bias, (const bf16*)residual, M, N_out, K / G2_BK,
+                                      tiles_m, tiles_n, up_row0);
+  if (le != cudaSuccess) return dl_set_error((int)le, "dl_linear(launch)");
+  DL_CHECK_LAUNCH("dl_linear");
+}
+
+// which tile width leaves the fewest idle pair-slots in the last wave: cost = waves x tile width
+static int g2_pick_bn(int M, int N, int n_pairs) {
+  const int tm = (M + 255) / 256;
+  auto cost = [&](int bn) {
+    const int tiles = tm * ((N + bn - 1) / bn);
+    return ((tiles + n_pairs - 1) / n_pairs) * bn;
+  };
+  return cost(128) < cost(256) ? 128 : 256;
+}
+
+extern "C" int dl_linear(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N, int K, int act,
+                         cudaStream_t stream) {
+  DL_REQUIRE(M >= 1 && N >= 8 && N % 8 == 0 && K >= G2_BK && K % G2_BK == 0 && act >= 0 && act <= 2 && (residual == nullptr || act == 0),
+             "dl_linear");
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int bn = g2_pick_bn(M, N, n_sm / 2 > 0 ? n_sm / 2 : 74);
+#define G2_GO(EPI)                                                                                              \
+  return bn == 256 ? g2_launch<256, EPI>(x, w, bias, residual, out, M, N, N, K, 0, stream)                      \
+                   : g2_launch<128, EPI>(x, w, bias, residual, out, M, N, N, K, 0, stream)
+  if (residual != nullptr) G2_GO(G2_EPI_RESIDUAL);
+  if (act == 1) G2_GO(G2_EPI_GELU);
+  if (act == 2) G2_GO(G2_EPI_QUICK_GELU);
+  G2_GO(G2_EPI_NONE);
+#undef G2_GO
+}
+
+extern "C" int dl_linear_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K, cudaStream_t stream) {
+  DL_REQUIRE(M >= 1 && I % 8 == 0 && K >= G2_BK && K % G2_BK == 0, "dl_linear_swiglu");
+  return g2_launch<256, G2_EPI_SWIGLU>(x, w_gate_up, nullptr, nullptr, act_out, M, 2 * I, I, K, I, stream);
+}

@@ -83,3 +83,41 @@ extern "C" int dl_predictor_mix(const void* y, void* g_scratch, void* z, int B, 
   predictor_mix_kernel<<<dim3(N, B), 128, 0, stream>>>((const bf16*)y, (const bf16*)g_scratch, (bf16*)z, N, C);
   DL_CHECK_LAUNCH("dl_predictor_mix");
 }
+
+// The predictors' 2-logit output heads (Linear(D/4 -> 2), DML:1345, :1383): N is far below a tensor-core tile and breaks the 16-byte row
+// stride TMA needs, so one warp per row does the N dot products (fp32 accumulate, + bias, one bf16 rounding like the bf16 nn.Linear).
+// out[m, n] = bf16(sum_k x[m, k] w[n, k] + b[n]);  N <= 8, K % 8 == 0.
+__global__ void __launch_bounds__(256) linear_tiny_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                          bf16* __restrict__ out, int M, int N, int K) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float acc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    float xv[8];
+    unpack8(ld8(x + (int64_t)m * K + k), xv);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (n < N) {
+        float wv[8];
+        unpack8(ld8(w + (int64_t)n * K + k), wv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[n] += xv[e] * wv[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    if (n < N) {
+      const float s = warp_sum(acc[n]);
+      if (lane == 0) out[(int64_t)m * N + n] = f2bf(s + (b != nullptr ? bf2f(b[n]) : 0.f));
+    }
+  }
+}
+extern "C" int dl_linear_tiny(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, cudaStream_t stream) {
+  DL_REQUIRE(N >= 1 && N <= 8 && K % 8 == 0, "dl_linear_tiny");
+  if (M == 0) return 0;
+  linear_tiny_kernel<<<(M + 7) / 8, 256, 0, stream>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, (bf16*)out, M, N, K);
+  DL_CHECK_LAUNCH("dl_linear_tiny");
+}

@@ -10,6 +10,8 @@
 // the fused consumer kernels in decode_fused.cu sum the slices in fixed order.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
@@ -190,9 +192,38 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle.
+// Encoding costs ~1-2 us of host time per map and a prefill issues ~700 TMA launches over buffers whose addresses repeat (torch's
+// caching allocator, the session's fixed decode buffers, the weights): a small per-thread direct-mapped cache keyed by every
+// parameter of the encoding returns the finished 128-byte descriptor instead (a descriptor is a pure function of its key).
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, stride;
+  uint32_t box_rows, box_cols;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && stride == o.stride && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct TmapEntry {
+  TmapKey key;
+  bool valid;
+  alignas(64) CUtensorMap map;
+};
+#define TMAP_CACHE_SLOTS 2048
+static thread_local TmapEntry* g_tmap_cache = nullptr;
+
 extern "C" int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                                uint32_t box_rows, uint32_t box_cols) {
+  if (g_tmap_cache == nullptr) g_tmap_cache = (TmapEntry*)calloc(TMAP_CACHE_SLOTS, sizeof(TmapEntry));
+  const TmapKey key = {base, rows, cols, row_stride_elems, box_rows, box_cols};
+  uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+  h ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols * 0x165667B19E3779F9ull) ^ ((uint64_t)box_rows << 40) ^ ((uint64_t)box_cols << 20) ^ row_stride_elems;
+  h ^= h >> 29;
+  TmapEntry* e = g_tmap_cache ? &g_tmap_cache[h % TMAP_CACHE_SLOTS] : nullptr;
+  if (e != nullptr && e->valid && e->key == key) {
+    memcpy(out_map, &e->map, sizeof(CUtensorMap));
+    return 0;
+  }
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (enc == nullptr) return dl_set_error(-2, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {cols, rows};
@@ -203,6 +234,11 @@ extern "C" int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, u
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return dl_set_error((int)r, "cuTensorMapEncodeTiled");
+  if (e != nullptr) {
+    e->key = key;
+    memcpy(&e->map, out_map, sizeof(CUtensorMap));
+    e->valid = true;
+  }
   return 0;
 }
 

@@ -218,6 +218,32 @@ class Engine:
         self.launches += 1
         return x
 
+    def linear(self, x2d, w, bias=None, act=0, residual=None, out=None):
+        """nn.Linear at q_len > 1 on the 2-CTA tcgen05 GEMM (csrc/gemm2.cu): out = act(x2d @ w.T + bias) (act 1: GELU-erf, 2: quick_gelu),
+        or with `residual` (may alias `out`): out = residual + (x2d @ w.T + bias) with the reference's two bf16 roundings."""
+        M, K = x2d.shape
+        N = w.shape[0]
+        assert x2d.is_contiguous() and w.is_contiguous() and w.shape[1] == K
+        if N < 8 or N % 8 or K % 64:
+            assert residual is None and act == 0 and N <= 8, (M, N, K)
+            out = torch.empty(M, N, device=x2d.device, dtype=x2d.dtype) if out is None else out
+            self.L.linear_tiny(_p(x2d), _p(w), _p(bias), _p(out), M, N, K, _stream())
+            self.launches += 1
+            return out
+        out = torch.empty(M, N, device=x2d.device, dtype=x2d.dtype) if out is None else out
+        self.L.linear(_p(x2d), _p(w), _p(bias), _p(residual), _p(out), M, N, K, act, _stream())
+        self.launches += 1
+        return out
+
+    def linear_swiglu(self, x2d, w_gate_up):
+        """LlamaMLP gate|up projection with act_fn(gate) * up in the GEMM epilogue (dynamic_modeling_llama.py:328)."""
+        M, K = x2d.shape
+        I = w_gate_up.shape[0] // 2
+        out = torch.empty(M, I, device=x2d.device, dtype=x2d.dtype)
+        self.L.linear_swiglu(_p(x2d), _p(w_gate_up), _p(out), M, I, K, _stream())
+        self.launches += 1
+        return out
+
     def attn_packed(self, qkv, B, N, heads, hd, causal=False):
         """non-causal attention over a fused [B*N, 3*heads*hd] projection (CLIP, predictor blocks)."""
         C = heads * hd
@@ -260,8 +286,7 @@ class Engine:
         cols = torch.empty(B * NP, pk["Kpad"], device=self.device, dtype=self.dtype)
         self.L.im2col_patches(_p(x), _p(cols), B, Cin, S, ps, pk["Kpad"], _stream())
         pe = torch.empty(B * NP, C, device=self.device, dtype=self.dtype)
-        self.L.gemm_bias_act(_p(cols), _p(pk["patch_w"]), None, _p(pe), B * NP, C, pk["Kpad"], 0, _stream())  # conv as a tcgen05 GEMM tile kernel
-        self.launches += 1
+        self.linear(cols, pk["patch_w"], out=pe)  # Conv2d(k = s = 14, bias=False) as an im2col GEMM
         tok = torch.empty(B * (NP + 1), C, device=self.device, dtype=self.dtype)
         self.L.clip_assemble(_p(pe), _p(vm.embeddings.class_embedding), _p(vm.embeddings.position_embedding.weight), _p(tok), B, NP, C, _stream())
         self.launches += 2
@@ -270,12 +295,12 @@ class Engine:
         for i in range(n_run):  # hidden_states[select_layer]: the layers after it are never needed
             lyr = vm.encoder.layers[i]
             y = self.layernorm(h, lyr.layer_norm1)
-            qkv = F.linear(y, pk["layers"][i]["wqkv"], pk["layers"][i]["bqkv"])
+            qkv = self.linear(y, pk["layers"][i]["wqkv"], pk["layers"][i]["bqkv"])
             a = self.attn_packed(qkv, B, NP + 1, nh, C // nh)
-            self.add_(h, F.linear(a, lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias))
+            self.linear(a, lyr.self_attn.out_proj.weight, lyr.self_attn.out_proj.bias, residual=h, out=h)  # residual in the epilogue
             y = self.layernorm(h, lyr.layer_norm2)
-            f = self.act_(F.linear(y, lyr.mlp.fc1.weight, lyr.mlp.fc1.bias), 2)
-            self.add_(h, F.linear(f, lyr.mlp.fc2.weight, lyr.mlp.fc2.bias))
+            f = self.linear(y, lyr.mlp.fc1.weight, lyr.mlp.fc1.bias, act=2)  # quick_gelu in the epilogue
+            self.linear(f, lyr.mlp.fc2.weight, lyr.mlp.fc2.bias, residual=h, out=h)
         if tower.select_feature == "patch":
             out = torch.empty(B, NP, C, device=self.device, dtype=self.dtype)
             self.L.drop_cls(_p(h), _p(out), B, NP, C, _stream())
@@ -293,10 +318,8 @@ class Engine:
         B, N, C = f.shape
         f = f.reshape(B * N, C).to(self.dtype)
         p = m.mm_projector
-        # plain dense GEMMs -> cuBLASLt (measured 3x faster than our 128x128 tcgen05 tile kernel at these shapes:
-        # profiles/r1_microbench_v6_gemm_tile.json); GELU is ours
-        y = self.act_(F.linear(f, p[0].weight, p[0].bias), 1)
-        y = F.linear(y, p[2].weight, p[2].bias)
+        y = self.linear(f, p[0].weight, p[0].bias, act=1)  # Linear + GELU(erf) in one launch
+        y = self.linear(y, p[2].weight, p[2].bias)
         return y.view(B, N, -1)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -313,24 +336,24 @@ class Engine:
         y = torch.empty(B * N, H, device=x.device, dtype=x.dtype)
         self.L.layernorm_strided(_p(x), _p(ln.weight), _p(ln.bias), _p(y), B, N, x.stride(0), H, ln.eps, _stream())
         self.launches += 1
-        y = self.act_(F.linear(y, mod.down_mlp[1].weight, mod.down_mlp[1].bias), 1)
+        y = self.linear(y, mod.down_mlp[1].weight, mod.down_mlp[1].bias, act=1)
         # `* image_policy`: the policy is all ones at inference (:1779-1785) -> exact identity in bf16
         for blk in mod.transformer:
             h = self.layernorm(y, blk.norm1)
-            qkv = F.linear(h, blk.attn.qkv.weight)
+            qkv = self.linear(h, blk.attn.qkv.weight)
             a = self.attn_packed(qkv, B, N, nh, D // nh)
-            self.add_(y, F.linear(a, blk.attn.proj.weight, blk.attn.proj.bias))
+            self.linear(a, blk.attn.proj.weight, blk.attn.proj.bias, residual=y, out=y)
             h = self.layernorm(y, blk.norm2)
-            f = self.act_(F.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias), 1)
-            self.add_(y, F.linear(f, blk.mlp.fc2.weight, blk.mlp.fc2.bias))
+            f = self.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=1)
+            self.linear(f, blk.mlp.fc2.weight, blk.mlp.fc2.bias, residual=y, out=y)
         z = torch.empty_like(y)
         g = torch.empty(B, D // 2, device=x.device, dtype=x.dtype)
         self.L.predictor_mix(_p(y), _p(g), _p(z), B, N, D, _stream())
         self.launches += 2
         o = mod.output_mlp
-        z = self.act_(F.linear(z, o[0].weight, o[0].bias), 1)
-        z = self.act_(F.linear(z, o[2].weight, o[2].bias), 1)
-        return F.linear(z, o[4].weight, o[4].bias).view(B, N, 2)
+        z = self.linear(z, o[0].weight, o[0].bias, act=1)
+        z = self.linear(z, o[2].weight, o[2].bias, act=1)
+        return self.linear(z, o[4].weight, o[4].bias).view(B, N, 2)
 
     @torch.no_grad()
     def text_predictor_forward(self, mod, x):
@@ -339,10 +362,10 @@ class Engine:
         x2 = x.reshape(-1, shp[-1]).contiguous()
         o = mod.output_mlp
         y = self.layernorm(x2, o[0])
-        y = self.act_(F.linear(y, o[1].weight, o[1].bias), 1)
-        y = self.act_(F.linear(y, o[3].weight, o[3].bias), 1)
-        y = self.act_(F.linear(y, o[5].weight, o[5].bias), 1)
-        return F.linear(y, o[7].weight, o[7].bias).view(*shp[:-1], 2)
+        y = self.linear(y, o[1].weight, o[1].bias, act=1)
+        y = self.linear(y, o[3].weight, o[3].bias, act=1)
+        y = self.linear(y, o[5].weight, o[5].bias, act=1)
+        return self.linear(y, o[7].weight, o[7].bias).view(*shp[:-1], 2)
 
     # ------------------------------------------------------------------------------------------------------------
     # multimodal splice  (dynamic_llava_arch.py:169-601, labels=None / attention_mask=None / one image per sample)
@@ -407,7 +430,7 @@ class Engine:
         K, V, cap = sess.arena.layer(l)
         kvl = sess.arena.kv_len[l]
         xn = self.rmsnorm(x, W["ln1"], c.rms_norm_eps)
-        qkv = F.linear(xn, W["wqkv"])
+        qkv = self.linear(xn, W["wqkv"])
         self.L.rope_append(_p(qkv), _p(pos), _p(cu), _p(kvl), None, _p(self.packed["cos"]), _p(self.packed["sin"]), _p(K), _p(V),
                            None, None, N, B, nh, hd, cap, _stream())
         attn = torch.empty(N, H, device=x.device, dtype=x.dtype)
@@ -421,13 +444,10 @@ class Engine:
             self.L.attn_varlen(_p(qkv), 3 * H, hd, _p(K), _p(V), nh * cap * hd, cap * hd, hd, 0, _p(attn), H, _p(cu), _p(kvl), B, nh,
                                hd, Lq, 1, scale, _stream())
         self.launches += 2
-        x.addmm_(attn, W["wo"].t())  # residual fused into the GEMM epilogue (beta = 1)
+        self.linear(attn, W["wo"], residual=x, out=x)  # x + o_proj(attn): bf16 projection, bf16 add, in the GEMM epilogue (:1289)
         xn = self.rmsnorm(x, W["ln2"], c.rms_norm_eps, out=xn)
-        gu = F.linear(xn, W["wgu"])
-        act = torch.empty(N, c.intermediate_size, device=x.device, dtype=x.dtype)
-        self.L.swiglu(_p(gu), _p(act), N, c.intermediate_size, _stream())
-        self.launches += 1
-        x.addmm_(act, W["wd"].t())
+        act = self.linear_swiglu(xn, W["wgu"])  # act_fn(gate) * up in the epilogue of the fused gate|up GEMM (:328)
+        self.linear(act, W["wd"], residual=x, out=x)  # (:1295)
         return x
 
     @torch.no_grad()
@@ -551,10 +571,10 @@ class Engine:
         a.floor_lo, a.floor_hi = a.host_len_lo, a.host_ub_hi  # every sample holds at least the prefill tokens from here on
         if all_logits:
             xn = self.rmsnorm(x, m.norm.weight, c.rms_norm_eps)
-            return F.linear(xn, self.model.lm_head.weight).view(B, Lq, -1)
+            return self.linear(xn, self.model.lm_head.weight).view(B, Lq, -1)
         last = x.view(B, Lq, H)[:, -1, :].contiguous()
         xn = self.rmsnorm(last, m.norm.weight, c.rms_norm_eps)
-        return F.linear(xn, self.model.lm_head.weight, out=None)
+        return self.linear(xn, self.model.lm_head.weight)
 
     @torch.no_grad()
     def continue_prefill(self, sess: Session, input_ids, record=None):
@@ -599,7 +619,7 @@ class Engine:
         if keep is not None:
             a.hi_exact = False
         xn = self.rmsnorm(x, m.norm.weight, c.rms_norm_eps)
-        return F.linear(xn, self.model.lm_head.weight).view(B, Tq, -1)
+        return self.linear(xn, self.model.lm_head.weight).view(B, Tq, -1)
 
     # ------------------------------------------------------------------------------------------------------------
     # decode step (q_len == 1): weight streaming + ragged attention, no host sync, CUDA-graph replayable

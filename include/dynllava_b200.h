@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DL_B200_ABI_VERSION 4  /* 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points;
+#define DL_B200_ABI_VERSION 5  /* 5: dl_linear / dl_linear_swiglu (2-CTA tcgen05 GEMM) replace dl_gemm_bias_act; 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points;
                                  * 4: no-KV-cache output sparsification (dl_output_rank / dl_output_keep_index) */
 
 int dl_version(void);
@@ -57,10 +57,20 @@ int dl_clip_assemble(const void* patch_embed, const void* cls, const void* pos, 
 /* multimodal_encoder/clip_encoder.py:43-51 (select_feature == "patch") */
 int dl_drop_cls(const void* x, void* out, int B, int NP, int C, cudaStream_t stream);
 
-/* K6: dense bf16 GEMM on TMA + tcgen05 tiles, out[M,N] = act(X[M,K] . W[N,K]^T + bias) (act 0 none, 1 GELU-erf on the bf16
- * rounded sum; bias may be NULL).  Conv2d patch embedding as an im2col GEMM (HF CLIPVisionEmbeddings) and the mlp2x_gelu
- * projector (multimodal_projector/builder.py:172-179).  K % 64 == 0, N % 8 == 0. */
-int dl_gemm_bias_act(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, int act, cudaStream_t stream);
+/* Dense bf16 GEMM for every nn.Linear at q_len > 1 — prefill q/k/v/o/gate/up/down (DML:377-392, :1011-1013, :1127, :294-330), lm_head
+ * over all positions (DML:2709), CLIP encoder linears + Conv2d patch embedding as an im2col GEMM (HF CLIPVisionEmbeddings /
+ * CLIPEncoderLayer), the mlp2x_gelu projector (multimodal_projector/builder.py:172-179), the predictor linears (DML:1324-1346,
+ * CTL:86-180): persistent 2-CTA (cta_group::2) tcgen05 tiles, TMA operand staging, double-buffered TMEM accumulators (gemm2.cu).
+ *   out[M,N] = epi(X[M,K] . W[N,K]^T + bias[N]);  act 0: none, 1: nn.GELU (erf) on the bf16-rounded sum, 2: HF quick_gelu;
+ *   residual != NULL (act must be 0): out = bf16(residual + bf16(X.W^T + bias)), residual [M,N] may alias out.
+ * bias / residual may be NULL.  K % 64 == 0, N % 8 == 0.  x, w, out contiguous row-major. */
+int dl_linear(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N, int K, int act,
+              cudaStream_t stream);
+/* LlamaMLP's gate|up projection with act_fn(gate) * up fused into the epilogue (DML:328): w_gate_up [2I,K] = [gate rows | up rows],
+ * act_out [M,I] = bf16(bf16(silu(bf16 g)) * bf16 u).  I % 128 == 0 recommended (7B: 11008 = 86*128, 13B: 13824 = 108*128). */
+int dl_linear_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K, cudaStream_t stream);
+/* The predictors' 2-logit heads (DML:1345, :1383): out[M,N] = bf16(X[M,K] . W[N,K]^T + bias), N <= 8, K % 8 == 0 (one warp per row). */
+int dl_linear_tiny(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, cudaStream_t stream);
 
 /* ---- K1: predictor score + top-k + gather/compact + index map + CSR header, DML:1867, :1897-1994 ------------- */
 /* logits [B,n_img,2]; forced_keep int64 [B,k] or NULL; hidden_in [B,P,H]; hidden_out [B,P',H], P' = P-n_img+k;

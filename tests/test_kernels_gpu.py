@@ -790,21 +790,108 @@ def test_skinny_gemm_swiglu_epilogue(L, M, I, K):
     assert (act.float().cpu() - want).abs().max() < 2e-2 * max(1.0, want.abs().max().item())
 
 
-@pytest.mark.parametrize("M,N,K,act,bias", [(4608, 1024, 640, 0, False), (32, 128, 640, 0, False), (4608, 4096, 1024, 1, True), (1152, 256, 128, 1, True),
-                                            (300, 1000, 192, 0, True)])
-def test_gemm_tcgen05_bias_act(L, M, N, K, act, bias):
+def _linear_ref(x, w, b, act, res):
+    """fp32 evaluation of the same bf16 inputs with the reference's rounding points (bf16 nn.Linear output, then the next bf16 op)"""
+    y = x.float() @ w.float().T
+    if b is not None:
+        y = y + b.float()
+    y = y.to(BF)
+    if act == 1:
+        return F.gelu(y.float()).to(BF)
+    if act == 2:  # HF quick_gelu on bf16 tensors
+        return (y * torch.sigmoid((1.702 * y.float()).to(BF).float()).to(BF)).to(BF)
+    if res is not None:
+        return (res.float() + y.float()).to(BF)
+    return y
+
+
+# (M, N, K, act, bias, residual): the prefill / CLIP / predictor / projector shapes (some shrunk along M), both tile widths (N = 4096 at
+# M = 1168 picks BN = 128), ragged M (1, 54, 300: partial and fully out-of-bounds half tiles), N not a multiple of the tile, K = 64
+@pytest.mark.parametrize("M,N,K,act,bias,res", [
+    (4608, 1024, 640, 0, False, False),    # CLIP patch embedding (im2col GEMM)
+    (1154, 3072, 1024, 0, True, False),    # CLIP q|k|v
+    (1154, 1024, 1024, 0, True, True),     # CLIP out_proj + residual
+    (1154, 4096, 1024, 2, True, False),    # CLIP fc1 + quick_gelu
+    (1154, 1024, 4096, 0, True, True),     # CLIP fc2 + residual
+    (1152, 4096, 1024, 1, True, False),    # projector fc1 + GELU
+    (1168, 12288, 4096, 0, False, False),  # prefill q|k|v (layers >= 2 of config 2)
+    (1168, 4096, 4096, 0, False, True),    # o_proj + residual (BN = 128)
+    (1168, 4096, 11008, 0, False, True),   # down_proj + residual, long K
+    (1214, 32000, 512, 0, False, False),   # lm_head over all positions (K shrunk)
+    (1152, 512, 4096, 1, True, False),     # predictor down_mlp
+    (1152, 1536, 512, 0, False, False),    # predictor block qkv (no bias)
+    (1152, 256, 512, 1, True, False),      # predictor output_mlp.0
+    (1152, 128, 256, 1, True, False),      # predictor output_mlp.2 (N = 128: one half-tile wide)
+    (300, 1000, 192, 0, True, False),      # nothing aligned
+    (54, 768, 256, 0, False, False),       # toy sizes: the second CTA of the pair is fully out of bounds
+    (1, 64, 64, 0, True, True),            # one row, one k-block
+    (257, 8, 64, 1, True, False),          # N = 8
+])
+def test_linear_2cta_tcgen05(L, M, N, K, act, bias, res):
     x, w = rnd(M, K, seed=150), rnd(N, K, seed=151, scale=0.05)
     b = rnd(N, seed=152, scale=0.1) if bias else None
-    out = torch.full((M, N), float("nan"), device=DEV, dtype=BF)
-    L.gemm_bias_act(P(x), P(w), P(b), P(out), M, N, K, act, ST())
+    r = rnd(M, N, seed=153) if res else None
+    if res:  # in place, as the engine uses it (residual stream updated by the epilogue)
+        out = r.to(DEV).clone()
+        L.linear(P(x), P(w), P(b), P(out), P(out), M, N, K, act, ST())
+    else:
+        out = torch.full((M, N), float("nan"), device=DEV, dtype=BF)
+        L.linear(P(x), P(w), P(b), None, P(out), M, N, K, act, ST())
     torch.cuda.synchronize()
-    y = x.float() @ w.float().T
-    if bias:
-        y = y + b.float()
-    ref = F.gelu(y.to(BF)).float() if act == 1 else y
+    ref = _linear_ref(x, w, b, act, r).float()
     got = out.float().cpu()
     assert torch.isfinite(got).all()
-    assert (got - ref).abs().max() < 1.5e-2 * max(1.0, ref.abs().max().item())
+    tol = 1.5e-2 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max() < tol, ((got - ref).abs().max().item(), tol)
+    # and against the library GEMM on the device: the same bf16 rounding of the same fp32 sums -> at most 1 ulp apart
+    lib = F.linear(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV))
+    if act == 0 and not res:
+        ulp_close(out, lib.cpu(), max_frac=0.02, abs_ok=2e-3)
+
+
+def test_linear_repeated_launches_and_determinism(L):
+    """persistent pairs + double-buffered TMEM: many tiles per pair, launched repeatedly on one stream, bit-identical every time"""
+    M, N, K = 4856, 4096, 1024
+    x, w = rnd(M, K, seed=160).to(DEV), rnd(N, K, seed=161, scale=0.05).to(DEV)
+    outs = []
+    for _ in range(4):
+        o = torch.empty(M, N, device=DEV, dtype=BF)
+        L.linear(P(x), P(w), None, None, P(o), M, N, K, 0, ST())
+        outs.append(o)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = (x.float() @ w.float().T)
+    assert (outs[0].float() - ref).abs().max() < 1.5e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,I,K", [(1168, 11008, 4096), (300, 512, 256), (54, 640, 128), (2048, 13824, 320)])
+def test_linear_swiglu_epilogue(L, M, I, K):
+    """gate|up GEMM with act_fn(gate) * up in the epilogue == the unfused pair (dl_linear + dl_swiglu) bit for bit, and the fp32 reference"""
+    x, w = rnd(M, K, seed=170), rnd(2 * I, K, seed=171, scale=0.05)
+    xd, wd = x.to(DEV), w.to(DEV)
+    act = torch.full((M, I), float("nan"), device=DEV, dtype=BF)
+    L.linear_swiglu(P(xd), P(wd), P(act), M, I, K, ST())
+    gu = torch.empty(M, 2 * I, device=DEV, dtype=BF)
+    L.linear(P(xd), P(wd), None, None, P(gu), M, 2 * I, K, 0, ST())
+    ref = torch.empty(M, I, device=DEV, dtype=BF)
+    L.swiglu(P(gu), P(ref), M, I, ST())
+    torch.cuda.synchronize()
+    assert torch.isfinite(act.float()).all()
+    assert torch.equal(act, ref), (act.float() - ref.float()).abs().max()
+    g32 = x.float() @ w.float().T
+    want = (F.silu(g32[:, :I].to(BF)) * g32[:, I:].to(BF)).float()
+    assert (act.float().cpu() - want).abs().max() < 2e-2 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(4608, 2, 128), (37, 2, 32), (5, 8, 64)])
+def test_linear_tiny_heads(L, M, N, K):
+    x, w, b = rnd(M, K, seed=180), rnd(N, K, seed=181, scale=0.1), rnd(N, seed=182, scale=0.1)
+    out = torch.empty(M, N, device=DEV, dtype=BF)
+    L.linear_tiny(P(x), P(w), P(b), P(out), M, N, K, ST())
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().T + b.float()).to(BF)
+    ulp_close(out, ref, max_frac=0.02)
 
 
 def test_skinny_gemm_split_heuristic(L):

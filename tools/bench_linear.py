@@ -1,0 +1,129 @@
+"""dl_linear (2-CTA tcgen05 GEMM, csrc/gemm2.cu) against the library GEMM (torch F.linear -> cuBLASLt) on every nn.Linear shape of the
+prefill / CLIP / predictor / projector path, timed inside one CUDA-graph replay (no host in the loop), weights rotated beyond L2 where
+they are small enough to matter.
+
+    python tools/bench_linear.py [--out gpurun_out/bench_linear.json] [--quick]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dynamic_llava_b200._lib import lib  # noqa: E402
+
+DEV, BF = "cuda", torch.bfloat16
+P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+ST = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def graph_ms(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+SHAPES = [  # name, M, N, K, kind
+    ("7B prefill qkv, layers 0-1 (M=8*607)", 4856, 12288, 4096, "plain"),
+    ("7B prefill o_proj+res, layers 0-1", 4856, 4096, 4096, "res"),
+    ("7B prefill gate|up+swiglu, layers 0-1", 4856, 11008, 4096, "swiglu"),
+    ("7B prefill down+res, layers 0-1", 4856, 4096, 11008, "res"),
+    ("7B prefill qkv, layers 2-31 (M=8*146)", 1168, 12288, 4096, "plain"),
+    ("7B prefill o_proj+res, layers 2-31", 1168, 4096, 4096, "res"),
+    ("7B prefill gate|up+swiglu, layers 2-31", 1168, 11008, 4096, "swiglu"),
+    ("7B prefill down+res, layers 2-31", 1168, 4096, 11008, "res"),
+    ("CLIP patch embed (M=8*576)", 4608, 1024, 640, "plain"),
+    ("CLIP qkv (M=8*577)", 4616, 3072, 1024, "bias"),
+    ("CLIP out_proj+res", 4616, 1024, 1024, "bias_res"),
+    ("CLIP fc1+quick_gelu", 4616, 4096, 1024, "bias_qgelu"),
+    ("CLIP fc2+res", 4616, 1024, 4096, "bias_res"),
+    ("projector fc1+gelu", 4608, 4096, 1024, "bias_gelu"),
+    ("projector fc2", 4608, 4096, 4096, "bias"),
+    ("predictor down_mlp+gelu", 4608, 512, 4096, "bias_gelu"),
+    ("predictor qkv", 4608, 1536, 512, "plain"),
+    ("predictor fc1+gelu", 4608, 2048, 512, "bias_gelu"),
+    ("predictor fc2+res", 4608, 512, 2048, "bias_res"),
+    ("13B cfg4 qkv layers 0-1 (M=4*2048)", 8192, 15360, 5120, "plain"),
+    ("13B cfg4 qkv layers 2-39 (M=4*1587)", 6348, 15360, 5120, "plain"),
+    ("13B cfg4 gate|up+swiglu layers 2-39", 6348, 13824, 5120, "swiglu"),
+    ("13B cfg4 down+res layers 2-39", 6348, 5120, 13824, "res"),
+    ("square 8192^3 (MEASURED_PEAKS shape)", 8192, 8192, 8192, "plain"),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_linear.json"))
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    L = lib()
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    burst, sust = float(pk.get("bf16_tflops", 1650.0)), float(pk.get("bf16_tflops_sustained", 1400.0))
+    rows = []
+    for name, M, N, K, kind in (SHAPES[:8] if a.quick else SHAPES):
+        g = torch.Generator(device=DEV).manual_seed(1)
+        x = torch.randn(M, K, device=DEV, dtype=BF, generator=g)
+        NW = 2 * N if kind == "swiglu" else N
+        w = (torch.randn(NW, K, device=DEV, dtype=BF, generator=g) * 0.02)
+        b = torch.randn(NW, device=DEV, dtype=BF, generator=g) * 0.1 if "bias" in kind else None
+        res = torch.randn(M, N, device=DEV, dtype=BF, generator=g) if "res" in kind else None
+        out = torch.empty(M, N, device=DEV, dtype=BF)
+        flop = 2.0 * M * NW * K
+        if kind == "swiglu":
+            ours = lambda: L.linear_swiglu(P(x), P(w), P(out), M, N, K, ST())
+            gu, act = torch.empty(M, NW, device=DEV, dtype=BF), torch.empty(M, N, device=DEV, dtype=BF)
+
+            def libfn():
+                torch.matmul(x, w.t(), out=gu)
+                L.swiglu(P(gu), P(act), M, N, ST())
+        else:
+            act_code = 1 if "gelu" in kind and "qgelu" not in kind else (2 if "qgelu" in kind else 0)
+            ours = lambda: L.linear(P(x), P(w), P(b), P(res), P(out if res is None else res), M, N, K, act_code, ST())
+            tmp = torch.empty(M, N, device=DEV, dtype=BF)
+
+            def libfn():  # what round 1 ran: library GEMM (+ bias) and the separate elementwise kernels
+                if res is not None and b is None:
+                    res.addmm_(x, w.t())
+                    return
+                y = F.linear(x, w, b)
+                if act_code:
+                    L.bias_act(P(y), None, M, N, act_code, ST())
+                if res is not None:
+                    L.add(P(res), P(y), M * N, ST())
+        ms_o = graph_ms(ours)
+        ms_l = graph_ms(libfn)
+        rows.append({"shape": name, "M": M, "N": NW, "K": K, "epilogue": kind, "ours_us": ms_o * 1e3, "ours_tflops": flop / ms_o / 1e9,
+                     "frac_of_burst": flop / ms_o / 1e9 / burst, "frac_of_sustained": flop / ms_o / 1e9 / sust,
+                     "library_path_us": ms_l * 1e3, "library_tflops": flop / ms_l / 1e9, "speedup_vs_library_path": ms_l / ms_o})
+        print(json.dumps(rows[-1]), flush=True)
+        del x, w, out
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump({"gpu": torch.cuda.get_device_name(0), "peaks": {"bf16_tflops": burst, "bf16_tflops_sustained": sust}, "rows": rows},
+              open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
