@@ -4,37 +4,47 @@
 // (q/k/v/o_proj), :1324-1346 (VisionPredictor linears), :2709 (lm_head); custom_transformer_layer.py:86-180 (predictor blocks);
 // multimodal_projector/builder.py:172-179; HF CLIPEncoderLayer / CLIPVisionEmbeddings (unvendored).
 //
-// B200 design: persistent kernel, one CTA per SM, CTAs paired into 2-CTA clusters that share one 256 x BN output tile
-// (`tcgen05.mma.cta_group::2`, M = 256, N = BN in {256, 128}).  Per pair and 64-wide k-block: each CTA TMA-loads ITS 128 rows of X and
-// ITS BN/2 rows of W (so every operand byte is fetched from L2 once per pair and each SM's tensor core reads only half of B from its
-// own shared memory); the leader CTA's single elected thread issues the MMAs for both SMs; accumulators live in TMEM, double
-// buffered (2 x BN columns), so the four epilogue warps of each CTA drain tile i (tcgen05.ld -> bias / activation / residual /
-// SwiGLU -> bf16 -> swizzled smem -> TMA store) while the tensor cores already run tile i+1.
-//   warp 0: TMA producer (6- or 8-stage mbarrier ring, both CTAs; completion bytes of BOTH CTAs land on the leader's `full` barrier)
+// B200 design: persistent kernel, one CTA per SM, CTAs paired into 2-CTA clusters that share one 256 x 256 output tile
+// (`tcgen05.mma.cta_group::2`, M = 256, N = 256).  Per pair and 64-wide k-block each CTA TMA-loads ITS 128 rows of X and ITS 128 rows
+// of W: every operand byte is fetched from L2 once per pair (64 B/clk/SM at the tensor peak — a 256 x 128 tile needs 96 B/clk/SM and
+// measured L2-bound) and each SM's tensor core reads only half of B from its own shared memory.  The leader CTA's single elected
+// thread issues the MMAs for both SMs; accumulators live in TMEM, double buffered (2 x 256 columns), so the eight epilogue warps of
+// each CTA drain segment i (tcgen05.ld -> bias / activation / residual / SwiGLU -> bf16 -> swizzled smem -> TMA store) while the
+// tensor cores already run segment i+1.
+//   warp 0: TMA producer (6-stage mbarrier ring, both CTAs; completion bytes of BOTH CTAs land on the leader's `full` barrier)
 //   warp 1: MMA issuer (leader CTA only) + TMEM allocation (both CTAs, cta_group::2)
-//   warps 2-5: epilogue (TMEM lane quarter = warp % 4)
+//   warps 2-9: epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 64-column chunks)
 // Barriers: full[s] (leader: 1 arrival + 2 x stage bytes), empty[s] (both CTAs, multicast tcgen05.commit), tmem_full[a] (both CTAs,
-// multicast commit), tmem_empty[a] (leader: 8 arrivals = 2 CTAs x 4 epilogue warps, the peer's arrive remotely through DSMEM).
-// Tiles are dealt round-robin to the pairs in bands of 8 m-tiles (m fastest inside a band) so that the pairs running concurrently
-// share W panels and an L2-sized band of X.
+// multicast commit), tmem_empty[a] (leader: 16 arrivals = 2 CTAs x 8 epilogue warps, the peer's arrive remotely through DSMEM).
+//
+// Work distribution is STREAM-K: the (tile, k-block) iteration space is cut into one contiguous, equally long range per pair, so no
+// pair idles in a last partial wave (M = 8 x 146 prefill rows give 80 tiles for 74 pairs: 2 waves tile-wise, 1.08 here).  A range
+// that starts inside a tile first computes that tile's tail k-blocks and parks the fp32 partial accumulator in the caller-provided
+// workspace (one slot per pair, per-warp release flags); the pair whose range holds the tile's k = 0 block finishes it: it adds the
+// parked partials of the following pairs (always already written: they are the FIRST thing those pairs do) in fixed order
+// (deterministic) and runs the epilogue.  Flags are reset by their single reader, so the workspace returns to all-zero after every
+// launch (CUDA-graph replayable).  Tiles are ordered in bands of 8 m-tiles (m fastest) so that concurrent pairs share W panels.
 #include <cuda.h>
 
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
 
 #define G2_BK 64
-#define G2_THREADS 192
+#define G2_BN 256
+#define G2_STAGES 6
+#define G2_EPI_WARPS 8
+#define G2_THREADS (32 * (2 + G2_EPI_WARPS))
+#define G2_SLOT_FLOATS (2 * 4 * 256 * 32)  // one pair's parked accumulator: 2 CTAs x 4 lane quarters x 256 columns x 32 lanes
+#define G2_SLOT_FLAGS 16                   // 2 CTAs x 8 epilogue warps
 
 enum { G2_EPI_NONE = 0, G2_EPI_GELU = 1, G2_EPI_QUICK_GELU = 2, G2_EPI_RESIDUAL = 3, G2_EPI_SWIGLU = 4 };
 
-template <int BN>
 struct G2Smem {
-  static constexpr int STAGES = BN == 256 ? 6 : 8;
-  alignas(1024) bf16 a[STAGES][128 * G2_BK];
-  alignas(1024) bf16 b[STAGES][(BN / 2) * G2_BK];
-  alignas(1024) uint8_t stage_out[4][2][4096];  // per epilogue warp: two 32-row x 64-column bf16 boxes (128B swizzle)
-  alignas(8) uint64_t full[STAGES];
-  alignas(8) uint64_t empty[STAGES];
+  alignas(1024) bf16 a[G2_STAGES][128 * G2_BK];
+  alignas(1024) bf16 b[G2_STAGES][128 * G2_BK];
+  alignas(1024) uint8_t stage_out[G2_EPI_WARPS][4096];  // per epilogue warp: one 32-row x 64-column bf16 box (128B swizzle)
+  alignas(8) uint64_t full[G2_STAGES];
+  alignas(8) uint64_t empty[G2_STAGES];
   alignas(8) uint64_t tmem_full[2];
   alignas(8) uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -93,6 +103,12 @@ DL_DEVINL void g2_tma_store_2d(const void* tmap, const void* smem_src, int c0, i
                "r"(c0), "r"(c1)
                : "memory");
 }
+DL_DEVINL int g2_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DL_DEVINL void g2_st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // tile -> (m-tile, n-tile): bands of 8 m-tiles, m fastest inside a band
 DL_DEVINL void g2_tile_coords(int tile, int tiles_m, int tiles_n, int& mt, int& nt) {
@@ -103,27 +119,43 @@ DL_DEVINL void g2_tile_coords(int tile, int tiles_m, int tiles_n, int& mt, int& 
   mt = band * 8 + (r - nt * m_in_band);
 }
 
+// work range of pair p in the linearised (tile, k-block) space [0, n_tiles * KB): stream-K cuts anywhere, otherwise at tile bounds
+struct G2Sched {
+  int n_tiles, KB, n_pairs, stream_k;
+  DL_DEVINL int begin(int p) const {
+    if (stream_k) return (int)(((int64_t)p * n_tiles * KB) / n_pairs);
+    return (int)(((int64_t)p * n_tiles) / n_pairs) * KB;
+  }
+};
+
 DL_DEVINL float g2_gelu_erf(float y) { return 0.5f * y * (1.0f + erff(y * 0.70710678118654752440f)); }
+DL_DEVINL float g2_sigmoid(float t) { return __fdividef(1.0f, 1.0f + __expf(-t)); }
 
 // EPI_SWIGLU: W = [gate rows (I) | up rows (I)]; the pair's B tile is gate rows [128 nt, +128) (CTA 0) and the matching up rows
 // (CTA 1), so accumulator columns [0,128) / [128,256) hold gate / up of the SAME 128 outputs; out is [M, I], N_out = I.
-template <int BN, int EPI>
+template <int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                               const __grid_constant__ CUtensorMap tmap_w,
                                                               const __grid_constant__ CUtensorMap tmap_o,
                                                               const bf16* __restrict__ bias, const bf16* residual, int M, int N_out,
-                                                              int KB, int tiles_m, int tiles_n, int up_row0) {
-  using Smem = G2Smem<BN>;
-  constexpr int STAGES = Smem::STAGES;
+                                                              int KB, int tiles_m, int tiles_n, int up_row0, float* ws_partial,
+                                                              int* ws_flags) {
+  constexpr int BN = G2_BN;
+  constexpr int STAGES = G2_STAGES;
   constexpr int TM_COLS = 2 * BN;
   constexpr uint32_t STAGE_BYTES = (128 + BN / 2) * G2_BK * 2;
   constexpr int OUT_W = EPI == G2_EPI_SWIGLU ? BN / 2 : BN;  // output columns per tile
   extern __shared__ uint8_t smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  G2Smem& S = *reinterpret_cast<G2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = g2_cluster_ctarank();
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int n_tiles = tiles_m * tiles_n;
+  const int pair = blockIdx.x >> 1;
+  G2Sched sched;
+  sched.n_tiles = tiles_m * tiles_n;
+  sched.KB = KB;
+  sched.n_pairs = gridDim.x >> 1;
+  sched.stream_k = ws_partial != nullptr;
+  const int g0 = sched.begin(pair), g1 = sched.begin(pair + 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -135,7 +167,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&S.tmem_full[a], 1);
-      mbar_init(&S.tmem_empty[a], 8);
+      mbar_init(&S.tmem_empty[a], 2 * G2_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -148,15 +180,18 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs) ------------------------------------------------
     if (elect_one()) {
+      // every CTA signals at its start, i.e. once it is resident: the dependent grid can only take SMs after ALL pairs run (a pair
+      // that waits for a parked partial must never wait for a pair that cannot be scheduled)
       pdl_launch_dependents();
       pdl_wait();  // X (and a residual) come from the predecessor kernel
       int it = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      for (int g = g0; g < g1;) {
+        const int tile = g / KB, kb0 = g - tile * KB, kb1 = min(KB, kb0 + (g1 - g));
         int mt, nt;
         g2_tile_coords(tile, tiles_m, tiles_n, mt, nt);
         const int m0 = mt * 256 + (int)rank * 128;
         const int n0 = EPI == G2_EPI_SWIGLU ? (rank == 0 ? nt * (BN / 2) : up_row0 + nt * (BN / 2)) : nt * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&S.empty[s], ph ^ 1);
@@ -165,48 +200,109 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           g2_tma_load_2d(S.a[s], &tmap_x, kb * G2_BK, m0, full_leader);
           g2_tma_load_2d(S.b[s], &tmap_w, kb * G2_BK, n0, full_leader);
         }
+        g += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (leader CTA) ------------------------------------------------
     if (rank == 0 && elect_one()) {
       constexpr uint32_t IDESC = umma_idesc_bf16(256, BN);
-      int it = 0, tc = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tc) {
-        const int a = tc & 1;
-        mbar_wait(&S.tmem_empty[a], ((tc >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+      int it = 0, sc = 0;
+      for (int g = g0; g < g1; ++sc) {
+        const int tile = g / KB, kb0 = g - tile * KB, kb1 = min(KB, kb0 + (g1 - g));
+        const int a = sc & 1;
+        mbar_wait(&S.tmem_empty[a], ((sc >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(a * BN);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&S.full[s], (it / STAGES) & 1);
           tc_fence_after();
           const uint64_t da = umma_desc_kmajor_sw128(smem_u32(S.a[s]));
           const uint64_t db = umma_desc_kmajor_sw128(smem_u32(S.b[s]));
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k) g2_umma(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < G2_BK / 16; ++k) g2_umma(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
           g2_commit_both(&S.empty[s]);  // the stage is free in both CTAs once these MMAs have read it
         }
         g2_commit_both(&S.tmem_full[a]);
+        g += kb1 - kb0;
       }
     }
   } else {
     // ------------------------------------------------ epilogue (both CTAs) ------------------------------------------------
-    const int q = warp & 3;  // TMEM lane quarter of this warp = rows [32q, 32q+32) of this CTA's half tile
-    uint8_t* stage0 = S.stage_out[q][0];
-    int tc = 0, nbox = 0;
-    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++tc) {
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter of this warp = rows [32q, 32q+32) of this CTA's half tile
+    const int hh = ew >> 2;   // which of the two warps of the quarter: takes the 64-column chunks c with c % 2 == hh
+    uint8_t* stage = S.stage_out[ew];
+    const int64_t my_part = ((int64_t)rank * 4 + q) * (256 * 32);  // float offset of this warp pair's region inside a slot
+    const int my_flag = (int)rank * 8 + ew;
+    int sc = 0;
+    for (int g = g0; g < g1; ++sc) {
+      const int tile = g / KB, kb0 = g - tile * KB, kb1 = min(KB, kb0 + (g1 - g));
+      g += kb1 - kb0;
       int mt, nt;
       g2_tile_coords(tile, tiles_m, tiles_n, mt, nt);
-      const int a = tc & 1;
+      const int a = sc & 1;
       const int row0 = mt * 256 + (int)rank * 128 + q * 32;
       const int row = row0 + lane;
       const int col_t = nt * OUT_W;
-      mbar_wait(&S.tmem_full[a], (tc >> 1) & 1);
-      tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+      const uint32_t tmem_empty_leader = g2_mapa(smem_u32(&S.tmem_empty[a]), 0);
+
+      if (kb0 > 0) {
+        // ---- this range started inside a tile: park the raw fp32 accumulator for the pair that finishes the tile ----
+        mbar_wait(&S.tmem_full[a], (sc >> 1) & 1);
+        tc_fence_after();
+        float* dst = ws_partial + (int64_t)pair * G2_SLOT_FLOATS + my_part;
 #pragma unroll 1
-      for (int c = 0; c < OUT_W / 64; ++c) {
+        for (int rc = hh; rc < BN / 64; rc += 2) {
+          uint32_t r[64];
+          tmem_ld_32x32b_x32(tacc + rc * 64, r);
+          tmem_ld_32x32b_x32(tacc + rc * 64 + 32, r + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 16; ++u)  // unit = 4 columns; 32 lanes x 16 B contiguous per unit
+            *reinterpret_cast<uint4*>(dst + ((rc * 16 + u) * 32 + lane) * 4) = make_uint4(r[u * 4], r[u * 4 + 1], r[u * 4 + 2], r[u * 4 + 3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          g2_mbar_arrive_cluster(tmem_empty_leader);
+          __threadfence();
+          g2_st_release(ws_flags + pair * G2_SLOT_FLAGS + my_flag, 1);
+        }
+        continue;
+      }
+
+      const bool gather = kb1 < KB;  // the tile's remaining k-blocks were computed (first thing) by the following pairs
+      if (gather) {
+        // wait until this warp's counterpart in every contributing pair has parked its slice
+        if (lane == 0) {
+          const int tile_end = (tile + 1) * KB;
+          for (int p2 = pair + 1;; ++p2) {
+            const int* f = ws_flags + p2 * G2_SLOT_FLAGS + my_flag;
+            while (g2_ld_acquire(f) == 0) {
+            }
+            if (sched.begin(p2 + 1) >= tile_end) break;
+          }
+        }
+        __syncwarp();
+      }
+      mbar_wait(&S.tmem_full[a], (sc >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = hh; c < OUT_W / 64; c += 2) {
+        const int col0 = col_t + c * 64;
+        // residual: the 32 x 64 box is fetched with 8 fully coalesced 16-byte loads per lane (4 rows x 128 B per instruction), issued
+        // before the TMEM loads so that their latency hides, then transposed through the staging box so each lane gets its own row
+        uint4 rres[8];
+        if constexpr (EPI == G2_EPI_RESIDUAL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = row0 + i * 4 + (lane >> 3), cc = col0 + (lane & 7) * 8;
+            rres[i] = (rr < M && cc < N_out) ? *reinterpret_cast<const uint4*>(residual + (int64_t)rr * N_out + cc) : make_uint4(0, 0, 0, 0);
+          }
+        }
         uint32_t r[64];
         uint32_t ru[EPI == G2_EPI_SWIGLU ? 64 : 1];
         tmem_ld_32x32b_x32(tacc + c * 64, r);
@@ -216,12 +312,51 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           tmem_ld_32x32b_x32(tacc + BN / 2 + c * 64 + 32, ru + 32);
         }
         tmem_ld_wait();
-        if (c == OUT_W / 64 - 1) {  // this warp has read its whole accumulator slice: hand the TMEM stage back to the MMA issuer
+        if (c + 2 >= OUT_W / 64) {  // this warp has read its whole accumulator slice: hand the TMEM stage back to the MMA issuer
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) g2_mbar_arrive_cluster(g2_mapa(smem_u32(&S.tmem_empty[a]), 0));
+          if (lane == 0) g2_mbar_arrive_cluster(tmem_empty_leader);
         }
-        const int col0 = col_t + c * 64;
+        if (gather) {
+          const int tile_end = (tile + 1) * KB;
+          for (int p2 = pair + 1;; ++p2) {  // fixed order: deterministic sums
+            const float* src = ws_partial + (int64_t)p2 * G2_SLOT_FLOATS + my_part;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(src + ((c * 16 + u) * 32 + lane) * 4));
+              r[u * 4] = __float_as_uint(__uint_as_float(r[u * 4]) + v.x);
+              r[u * 4 + 1] = __float_as_uint(__uint_as_float(r[u * 4 + 1]) + v.y);
+              r[u * 4 + 2] = __float_as_uint(__uint_as_float(r[u * 4 + 2]) + v.z);
+              r[u * 4 + 3] = __float_as_uint(__uint_as_float(r[u * 4 + 3]) + v.w);
+            }
+            if constexpr (EPI == G2_EPI_SWIGLU) {
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (((c + 2) * 16 + u) * 32 + lane) * 4));
+                ru[u * 4] = __float_as_uint(__uint_as_float(ru[u * 4]) + v.x);
+                ru[u * 4 + 1] = __float_as_uint(__uint_as_float(ru[u * 4 + 1]) + v.y);
+                ru[u * 4 + 2] = __float_as_uint(__uint_as_float(ru[u * 4 + 2]) + v.z);
+                ru[u * 4 + 3] = __float_as_uint(__uint_as_float(ru[u * 4 + 3]) + v.w);
+              }
+            }
+            if (sched.begin(p2 + 1) >= tile_end) break;
+          }
+        }
+        // the TMA store that last used this warp's staging box has read it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        bf16x8 resrow[EPI == G2_EPI_RESIDUAL ? 8 : 1];
+        if constexpr (EPI == G2_EPI_RESIDUAL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+            *reinterpret_cast<uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4)) = rres[i];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) resrow[j] = *reinterpret_cast<const bf16x8*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4));
+          __syncwarp();
+        }
         bf16x8 pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -242,38 +377,40 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float y = rbf(f[u]);
-              const float t = rbf(1.702f * y);
-              const float sg = rbf(1.0f / (1.0f + expf(-t)));
-              f[u] = y * sg;
+              f[u] = y * rbf(g2_sigmoid(rbf(1.702f * y)));
             }
           } else if constexpr (EPI == G2_EPI_RESIDUAL) {  // x + linear(...): bf16 linear output, then a bf16 add (:1289, :1295)
-            if (row < M && col < N_out) {
-              float rv[8];
-              unpack8(ld8(residual + (int64_t)row * N_out + col), rv);
+            float rv[8];
+            unpack8(resrow[j], rv);
 #pragma unroll
-              for (int u = 0; u < 8; ++u) f[u] = rbf(f[u]) + rv[u];
-            }
+            for (int u = 0; u < 8; ++u) f[u] = rbf(f[u]) + rv[u];
           } else if constexpr (EPI == G2_EPI_SWIGLU) {  // bf16(bf16(silu(bf16 g)) * bf16 u)  (:328)
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              const float g = rbf(f[u]), up = rbf(__uint_as_float(ru[j * 8 + u]));
-              f[u] = rbf(g / (1.0f + expf(-g))) * up;
+              const float gt = rbf(f[u]), up = rbf(__uint_as_float(ru[j * 8 + u]));
+              f[u] = rbf(gt * g2_sigmoid(gt)) * up;
             }
           }
           pk[j] = pack8(f);
         }
-        uint8_t* stage = stage0 + (nbox & 1) * 4096;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store that last used THIS box has read it
-        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) *reinterpret_cast<bf16x8*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = pk[j];
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && row0 < M && col0 < N_out) {  // the tensor map clips rows >= M and columns >= N_out
-          g2_tma_store_2d(&tmap_o, stage, col0, row0);
+        if (lane == 0) {
+          if (row0 < M && col0 < N_out) g2_tma_store_2d(&tmap_o, stage, col0, row0);  // the tensor map clips rows >= M, columns >= N_out
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // (possibly empty) group: keeps the 2-deep accounting uniform
-        ++nbox;
+      }
+      if (gather) {  // single reader of these flags: hand them back zeroed (the workspace is all-zero again after the launch)
+        __syncwarp();
+        if (lane == 0) {
+          const int tile_end = (tile + 1) * KB;
+          for (int p2 = pair + 1;; ++p2) {
+            ws_flags[p2 * G2_SLOT_FLAGS + my_flag] = 0;
+            if (sched.begin(p2 + 1) >= tile_end) break;
+          }
+        }
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -284,31 +421,58 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI>
-static int g2_launch(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N_w, int N_out, int K,
-                     int up_row0, cudaStream_t stream) {
-  alignas(64) CUtensorMap tx, tw, to;
-  int rc = dl_make_tmap_2d(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, G2_BK);
-  if (rc) return rc;
-  rc = dl_make_tmap_2d(&tw, w, (uint64_t)N_w, (uint64_t)K, (uint64_t)K, BN / 2, G2_BK);
-  if (rc) return rc;
-  rc = dl_make_tmap_2d(&to, out, (uint64_t)M, (uint64_t)N_out, (uint64_t)N_out, 32, 64);
-  if (rc) return rc;
-  const int smem = (int)sizeof(G2Smem<BN>) + 1024;
-  static bool attr_set = false;
+static int g2_num_sms() {
   static int n_sm = 0;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return dl_set_error((int)e, "dl_linear(smem attr)");
+  if (n_sm == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  return n_sm;
+}
+
+extern "C" int64_t dl_linear_workspace_bytes(void) {
+  const int64_t slots = g2_num_sms() / 2 + 1;
+  return slots * (int64_t)(G2_SLOT_FLOATS * sizeof(float) + G2_SLOT_FLAGS * sizeof(int));
+}
+
+template <int EPI>
+static int g2_launch(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N_w, int N_out, int K,
+                     int up_row0, void* workspace, cudaStream_t stream) {
+  alignas(64) CUtensorMap tx, tw, to;
+  int rc = dl_make_tmap_2d(&tx, x, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, G2_BK);
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&tw, w, (uint64_t)N_w, (uint64_t)K, (uint64_t)K, G2_BN / 2, G2_BK);
+  if (rc) return rc;
+  rc = dl_make_tmap_2d(&to, out, (uint64_t)M, (uint64_t)N_out, (uint64_t)N_out, 32, 64);
+  if (rc) return rc;
+  const int smem = (int)sizeof(G2Smem) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return dl_set_error((int)e, "dl_linear(smem attr)");
     attr_set = true;
   }
-  constexpr int OUT_W = EPI == G2_EPI_SWIGLU ? BN / 2 : BN;
+  constexpr int OUT_W = EPI == G2_EPI_SWIGLU ? G2_BN / 2 : G2_BN;
   const int tiles_m = (M + 255) / 256, tiles_n = (N_out + OUT_W - 1) / OUT_W;
-  int n_pairs = n_sm / 2;
-  if (n_pairs > tiles_m * tiles_n) n_pairs = tiles_m * tiles_n;
+  const int KB = K / G2_BK;
+  const int64_t total = (int64_t)tiles_m * tiles_n * KB;
+  int n_pairs = g2_num_sms() / 2;
+  float* ws_partial = nullptr;
+  int* ws_flags = nullptr;
+  if (workspace != nullptr) {
+    // stream-K (equal (tile, k-block) ranges) when it beats whole tiles per pair: cost in k-block times, a parked + gathered partial
+    // charged as ~8 of them (measured order of magnitude: 256 KB through L2 each way plus the flag round trip)
+    const int n_tiles = tiles_m * tiles_n;
+    const int64_t cost_tiles = (int64_t)((n_tiles + n_pairs - 1) / n_pairs) * KB;
+    const int64_t cost_sk = (total + n_pairs - 1) / n_pairs + 8;
+    if (n_tiles % n_pairs != 0 && cost_sk < cost_tiles && total / n_pairs >= 4) {
+      ws_partial = (float*)workspace;
+      ws_flags = (int*)((uint8_t*)workspace + (int64_t)(g2_num_sms() / 2 + 1) * G2_SLOT_FLOATS * sizeof(float));
+    }
+  }
+  if (ws_partial == nullptr && n_pairs > tiles_m * tiles_n) n_pairs = tiles_m * tiles_n;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * n_pairs);
   cfg.blockDim = dim3(G2_THREADS);
@@ -323,44 +487,24 @@ static int g2_launch(const void* x, const void* w, const void* bias, const void*
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, EPI>, tx, tw, to, (const bf16*)bias, (const bf16*)residual, M, N_out, K / G2_BK,
-                                      tiles_m, tiles_n, up_row0);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI>, tx, tw, to, (const bf16*)bias, (const bf16*)residual, M, N_out, KB, tiles_m,
+                                      tiles_n, up_row0, ws_partial, ws_flags);
   if (le != cudaSuccess) return dl_set_error((int)le, "dl_linear(launch)");
   DL_CHECK_LAUNCH("dl_linear");
 }
 
-// which tile width leaves the fewest idle pair-slots in the last wave: cost = waves x tile width
-static int g2_pick_bn(int M, int N, int n_pairs) {
-  const int tm = (M + 255) / 256;
-  auto cost = [&](int bn) {
-    const int tiles = tm * ((N + bn - 1) / bn);
-    return ((tiles + n_pairs - 1) / n_pairs) * bn;
-  };
-  return cost(128) < cost(256) ? 128 : 256;
-}
-
 extern "C" int dl_linear(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N, int K, int act,
-                         cudaStream_t stream) {
+                         void* workspace, cudaStream_t stream) {
   DL_REQUIRE(M >= 1 && N >= 8 && N % 8 == 0 && K >= G2_BK && K % G2_BK == 0 && act >= 0 && act <= 2 && (residual == nullptr || act == 0),
              "dl_linear");
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
-  const int bn = g2_pick_bn(M, N, n_sm / 2 > 0 ? n_sm / 2 : 74);
-#define G2_GO(EPI)                                                                                              \
-  return bn == 256 ? g2_launch<256, EPI>(x, w, bias, residual, out, M, N, N, K, 0, stream)                      \
-                   : g2_launch<128, EPI>(x, w, bias, residual, out, M, N, N, K, 0, stream)
-  if (residual != nullptr) G2_GO(G2_EPI_RESIDUAL);
-  if (act == 1) G2_GO(G2_EPI_GELU);
-  if (act == 2) G2_GO(G2_EPI_QUICK_GELU);
-  G2_GO(G2_EPI_NONE);
-#undef G2_GO
+  if (residual != nullptr) return g2_launch<G2_EPI_RESIDUAL>(x, w, bias, residual, out, M, N, N, K, 0, workspace, stream);
+  if (act == 1) return g2_launch<G2_EPI_GELU>(x, w, bias, nullptr, out, M, N, N, K, 0, workspace, stream);
+  if (act == 2) return g2_launch<G2_EPI_QUICK_GELU>(x, w, bias, nullptr, out, M, N, N, K, 0, workspace, stream);
+  return g2_launch<G2_EPI_NONE>(x, w, bias, nullptr, out, M, N, N, K, 0, workspace, stream);
 }
 
-extern "C" int dl_linear_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K, cudaStream_t stream) {
+extern "C" int dl_linear_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K, void* workspace,
+                                cudaStream_t stream) {
   DL_REQUIRE(M >= 1 && I % 8 == 0 && K >= G2_BK && K % G2_BK == 0, "dl_linear_swiglu");
-  return g2_launch<256, G2_EPI_SWIGLU>(x, w_gate_up, nullptr, nullptr, act_out, M, 2 * I, I, K, I, stream);
+  return g2_launch<G2_EPI_SWIGLU>(x, w_gate_up, nullptr, nullptr, act_out, M, 2 * I, I, K, I, workspace, stream);
 }

@@ -101,6 +101,8 @@ class Engine:
         self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
         self.attn_early_kv = os.environ.get("DLB200_ATTN_EARLY_KV", "1") == "1"  # fetch prefill-time K/V tiles before the PDL wait
         self.attn_prefetch_wo = os.environ.get("DLB200_ATTN_PREFETCH_WO", "0") == "1"  # o_proj weight -> L2 during decode attention (measured: no gain)
+        # stream-K workspace of dl_linear (parked partial accumulators + flags): zeroed once, used by the main stream's launches only
+        self.gemm_ws = torch.zeros(self.L.linear_workspace_bytes(), device=self.device, dtype=torch.uint8)
         self.launches = 0  # kernels of OURS launched (eager path; graph replays counted via launches_per_step)
         self.launches_per_step = 0
 
@@ -231,7 +233,7 @@ class Engine:
             self.launches += 1
             return out
         out = torch.empty(M, N, device=x2d.device, dtype=x2d.dtype) if out is None else out
-        self.L.linear(_p(x2d), _p(w), _p(bias), _p(residual), _p(out), M, N, K, act, _stream())
+        self.L.linear(_p(x2d), _p(w), _p(bias), _p(residual), _p(out), M, N, K, act, _p(self.gemm_ws), _stream())
         self.launches += 1
         return out
 
@@ -240,7 +242,7 @@ class Engine:
         M, K = x2d.shape
         I = w_gate_up.shape[0] // 2
         out = torch.empty(M, I, device=x2d.device, dtype=x2d.dtype)
-        self.L.linear_swiglu(_p(x2d), _p(w_gate_up), _p(out), M, I, K, _stream())
+        self.L.linear_swiglu(_p(x2d), _p(w_gate_up), _p(out), M, I, K, _p(self.gemm_ws), _stream())
         self.launches += 1
         return out
 

@@ -63,12 +63,16 @@ int dl_drop_cls(const void* x, void* out, int B, int NP, int C, cudaStream_t str
  * CTL:86-180): persistent 2-CTA (cta_group::2) tcgen05 tiles, TMA operand staging, double-buffered TMEM accumulators (gemm2.cu).
  *   out[M,N] = epi(X[M,K] . W[N,K]^T + bias[N]);  act 0: none, 1: nn.GELU (erf) on the bf16-rounded sum, 2: HF quick_gelu;
  *   residual != NULL (act must be 0): out = bf16(residual + bf16(X.W^T + bias)), residual [M,N] may alias out.
- * bias / residual may be NULL.  K % 64 == 0, N % 8 == 0.  x, w, out contiguous row-major. */
+ * bias / residual may be NULL.  K % 64 == 0, N % 8 == 0.  x, w, out contiguous row-major.
+ * workspace (or NULL): dl_linear_workspace_bytes() bytes of device memory, ZEROED once by the caller and then owned by the calls of
+ * one stream: enables stream-K work distribution (equal (tile, k-block) ranges per CTA pair; partial accumulators of split tiles are
+ * parked there and added in fixed order: deterministic); every launch leaves it zeroed again.  NULL: whole tiles per pair. */
+int64_t dl_linear_workspace_bytes(void);
 int dl_linear(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N, int K, int act,
-              cudaStream_t stream);
+              void* workspace, cudaStream_t stream);
 /* LlamaMLP's gate|up projection with act_fn(gate) * up fused into the epilogue (DML:328): w_gate_up [2I,K] = [gate rows | up rows],
  * act_out [M,I] = bf16(bf16(silu(bf16 g)) * bf16 u).  I % 128 == 0 recommended (7B: 11008 = 86*128, 13B: 13824 = 108*128). */
-int dl_linear_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K, cudaStream_t stream);
+int dl_linear_swiglu(const void* x, const void* w_gate_up, void* act_out, int M, int I, int K, void* workspace, cudaStream_t stream);
 /* The predictors' 2-logit heads (DML:1345, :1383): out[M,N] = bf16(X[M,K] . W[N,K]^T + bias), N <= 8, K % 8 == 0 (one warp per row). */
 int dl_linear_tiny(const void* x, const void* w, const void* bias, void* out, int M, int N, int K, cudaStream_t stream);
 

@@ -790,6 +790,17 @@ def test_skinny_gemm_swiglu_epilogue(L, M, I, K):
     assert (act.float().cpu() - want).abs().max() < 2e-2 * max(1.0, want.abs().max().item())
 
 
+def _linear_ws(L):
+    return torch.zeros(L.linear_workspace_bytes(), device=DEV, dtype=torch.uint8)
+
+
+def _linear_ws_flag_offset(L):
+    """int32 index where the flag words start: slots * 2*4*256*32 floats of parked accumulators come first (csrc/gemm2.cu)"""
+    n = L.linear_workspace_bytes()
+    slots = n // (2 * 4 * 256 * 32 * 4 + 16 * 4)
+    return slots * 2 * 4 * 256 * 32
+
+
 def _linear_ref(x, w, b, act, res):
     """fp32 evaluation of the same bf16 inputs with the reference's rounding points (bf16 nn.Linear output, then the next bf16 op)"""
     y = x.float() @ w.float().T
@@ -827,17 +838,21 @@ def _linear_ref(x, w, b, act, res):
     (1, 64, 64, 0, True, True),            # one row, one k-block
     (257, 8, 64, 1, True, False),          # N = 8
 ])
-def test_linear_2cta_tcgen05(L, M, N, K, act, bias, res):
+@pytest.mark.parametrize("stream_k", [False, True])
+def test_linear_2cta_tcgen05(L, M, N, K, act, bias, res, stream_k):
+    ws = _linear_ws(L) if stream_k else None
     x, w = rnd(M, K, seed=150), rnd(N, K, seed=151, scale=0.05)
     b = rnd(N, seed=152, scale=0.1) if bias else None
     r = rnd(M, N, seed=153) if res else None
     if res:  # in place, as the engine uses it (residual stream updated by the epilogue)
         out = r.to(DEV).clone()
-        L.linear(P(x), P(w), P(b), P(out), P(out), M, N, K, act, ST())
+        L.linear(P(x), P(w), P(b), P(out), P(out), M, N, K, act, P(ws), ST())
     else:
         out = torch.full((M, N), float("nan"), device=DEV, dtype=BF)
-        L.linear(P(x), P(w), P(b), None, P(out), M, N, K, act, ST())
+        L.linear(P(x), P(w), P(b), None, P(out), M, N, K, act, P(ws), ST())
     torch.cuda.synchronize()
+    if ws is not None:
+        assert int(ws.view(torch.int32)[_linear_ws_flag_offset(L):].abs().sum()) == 0  # flags handed back zeroed
     ref = _linear_ref(x, w, b, act, r).float()
     got = out.float().cpu()
     assert torch.isfinite(got).all()
@@ -854,31 +869,63 @@ def test_linear_repeated_launches_and_determinism(L):
     M, N, K = 4856, 4096, 1024
     x, w = rnd(M, K, seed=160).to(DEV), rnd(N, K, seed=161, scale=0.05).to(DEV)
     outs = []
-    for _ in range(4):
-        o = torch.empty(M, N, device=DEV, dtype=BF)
-        L.linear(P(x), P(w), None, None, P(o), M, N, K, 0, ST())
-        outs.append(o)
+    ws = _linear_ws(L)
+    for sk in (None, ws):
+        outs = []
+        for _ in range(4):
+            o = torch.empty(M, N, device=DEV, dtype=BF)
+            L.linear(P(x), P(w), None, None, P(o), M, N, K, 0, P(sk), ST())
+            outs.append(o)
+        torch.cuda.synchronize()
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0])
+        ref = (x.float() @ w.float().T)
+        assert (outs[0].float() - ref).abs().max() < 1.5e-2 * ref.abs().max().item()
+
+
+def test_linear_stream_k_in_cuda_graph(L):
+    """the parked-partial flags are reset by their reader, so a captured launch replays correctly any number of times"""
+    M, N, K = 1168, 4096, 4096
+    x, w = rnd(M, K, seed=162).to(DEV), rnd(N, K, seed=163, scale=0.05).to(DEV)
+    ws = _linear_ws(L)
+    o = torch.zeros(M, N, device=DEV, dtype=BF)
+    L.linear(P(x), P(w), None, None, P(o), M, N, K, 0, P(ws), ST())
     torch.cuda.synchronize()
-    for o in outs[1:]:
-        assert torch.equal(o, outs[0])
-    ref = (x.float() @ w.float().T)
-    assert (outs[0].float() - ref).abs().max() < 1.5e-2 * ref.abs().max().item()
+    first = o.clone()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(3):
+                L.linear(P(x), P(w), None, None, P(o), M, N, K, 0, P(ws), ctypes.c_void_p(side.cuda_stream))
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(o, first)
+    assert int(ws.view(torch.int32)[_linear_ws_flag_offset(L):].abs().sum()) == 0
 
 
 @pytest.mark.parametrize("M,I,K", [(1168, 11008, 4096), (300, 512, 256), (54, 640, 128), (2048, 13824, 320)])
-def test_linear_swiglu_epilogue(L, M, I, K):
+@pytest.mark.parametrize("stream_k", [False, True])
+def test_linear_swiglu_epilogue(L, M, I, K, stream_k):
     """gate|up GEMM with act_fn(gate) * up in the epilogue == the unfused pair (dl_linear + dl_swiglu) bit for bit, and the fp32 reference"""
     x, w = rnd(M, K, seed=170), rnd(2 * I, K, seed=171, scale=0.05)
     xd, wd = x.to(DEV), w.to(DEV)
     act = torch.full((M, I), float("nan"), device=DEV, dtype=BF)
-    L.linear_swiglu(P(xd), P(wd), P(act), M, I, K, ST())
+    L.linear_swiglu(P(xd), P(wd), P(act), M, I, K, P(_linear_ws(L)) if stream_k else None, ST())
     gu = torch.empty(M, 2 * I, device=DEV, dtype=BF)
-    L.linear(P(xd), P(wd), None, None, P(gu), M, 2 * I, K, 0, ST())
+    L.linear(P(xd), P(wd), None, None, P(gu), M, 2 * I, K, 0, None, ST())
     ref = torch.empty(M, I, device=DEV, dtype=BF)
     L.swiglu(P(gu), P(ref), M, I, ST())
     torch.cuda.synchronize()
     assert torch.isfinite(act.float()).all()
-    assert torch.equal(act, ref), (act.float() - ref.float()).abs().max()
+    if stream_k:  # a split K changes the fp32 summation order: equal up to a last-place rounding
+        ulp_close(act, ref, max_frac=0.02, abs_ok=2e-3)
+    else:
+        assert torch.equal(act, ref), (act.float() - ref.float()).abs().max()
     g32 = x.float() @ w.float().T
     want = (F.silu(g32[:, :I].to(BF)) * g32[:, I:].to(BF)).float()
     assert (act.float().cpu() - want).abs().max() < 2e-2 * max(1.0, want.abs().max().item())
