@@ -91,10 +91,21 @@ __global__ void __launch_bounds__(SG_THREADS) skinny_gemm_kernel(const __grid_co
       }
       // ...and ask the TMA unit to pull the next `l2_pf` W tiles of this CTA into the 126 MB L2 (no smem needed), so HBM
       // keeps streaming weights while the small predecessor kernel (norm / SwiGLU / attention) is still running.
-      const int npf = min(nkb, npre + l2_pf);
-      for (int i = npre; i < npf; ++i) tma_prefetch_2d(&tmap_w, (kb0 + i) * SG_BK, EPI == 1 ? g0 : n0);
+      // l2_pf > 0: ahead of the wait (measured negative in round 1: competes with the predecessor's own stream);
+      // l2_pf < 0: right AFTER the wait, i.e. exactly when the predecessor has finished and HBM would otherwise idle until the
+      // first X tile arrives and the MMAs start freeing ring stages (round 2: also measured neutral, 2.73-2.78 ms per decode step for
+      // 0 / 12 / 24 / 48 MB, profiles/r2_l2_prefetch_after_wait.md)
+      const int npf = min(nkb, npre + (l2_pf > 0 ? l2_pf : -l2_pf));
+      if (l2_pf > 0)
+        for (int i = npre; i < npf; ++i) tma_prefetch_2d(&tmap_w, (kb0 + i) * SG_BK, EPI == 1 ? g0 : n0);
       pdl_launch_dependents();
       pdl_wait();
+      if (l2_pf < 0) {
+        for (int i = npre; i < npf; ++i) {
+          tma_prefetch_2d(&tmap_w, (kb0 + i) * SG_BK, EPI == 1 ? g0 : n0);
+          if constexpr (EPI == 1) tma_prefetch_2d(&tmap_w, (kb0 + i) * SG_BK, I_rows + g0);
+        }
+      }
       for (int i = 0; i < npre; ++i) tma_load_2d(S.b[i], &tmap_x, (kb0 + i) * SG_BK, 0, &S.full[i]);
       for (int i = npre; i < nkb; ++i) {
         const int s = i % SG_STAGES;
@@ -253,8 +264,11 @@ static int launch_sg(const CUtensorMap& tw, const CUtensorMap& tx, float* partia
     attr_set = true;
   }
   dim3 grid((N + SG_BM - 1) / SG_BM, splits);
-  const int64_t budget = (int64_t)(l2_prefetch_mb < 0 ? 0 : l2_prefetch_mb) << 20;  // total bytes prefetched ahead into L2 (default: off)
-  const int l2_pf = (int)(budget / ((int64_t)grid.x * grid.y * SG_BM * SG_BK * 2));
+  // l2_prefetch_mb: 0 / -1 = off; > 0 = MB per launch prefetched into L2 BEFORE the dependency wait; < -1 = |mb| MB AFTER the wait
+  const int64_t mb = l2_prefetch_mb == -1 ? 0 : l2_prefetch_mb;
+  const int64_t budget = (mb < 0 ? -mb : mb) << 20;
+  int l2_pf = (int)(budget / ((int64_t)grid.x * grid.y * SG_BM * SG_BK * 2));
+  if (mb < 0) l2_pf = -l2_pf;
   cudaError_t le = dl_launch_pdl(skinny_gemm_kernel<NB, EPI>, grid, dim3(SG_THREADS), (size_t)smem, stream, tw, tx, partial, M, N, KB, kbps,
                                  l2_pf, act_out);
   if (le != cudaSuccess) return dl_set_error((int)le, "dl_skinny_gemm(launch)");
