@@ -69,7 +69,7 @@ class DynLlavaLib:
 
         def call(*args):
             rc = raw(*args)
-            if raw.restype is ctypes.c_int and rc != 0 and name not in ("version", "device_is_sm100", "skinny_gemm_splits", "dec_gemm_residual_parts"):
+            if raw.restype is ctypes.c_int and rc != 0 and name not in ("version", "device_is_sm100", "skinny_gemm_splits"):
                 raise RuntimeError(f"dl_{name} failed ({rc}): {self._dl_last_error_string().decode()}")
             return rc
 

@@ -29,7 +29,6 @@ SOURCES = [
     "skinny_gemm.cu",
     "gemm2.cu",
     "decode_fused.cu",
-    "dec_gemm.cu",
     "predictor_ops.cu",
     "sample.cu",
     "nocache_select.cu",

@@ -52,10 +52,6 @@ struct AdFused {
   // written long before this decode step, so (n_split == 1 only) the producer may start their TMA loads BEFORE
   // griddepcontrol.wait, overlapping the K/V fetch with the tail of the QKV GEMM.
   int len_floor;
-  // decode step with the QKV GEMM's epilogue doing reduce + RoPE + write (dec_gemm.cu): q comes from a [B, H] buffer and the new
-  // token's k / v already sit in the arena at slot kv_len[b], so the token is simply key number kv_len[b] of the stream.  If the
-  // token is not kept (keep[b] == 0) the slot is zeroed again afterwards: slots at or beyond kv_len stay zero (cache.py invariant).
-  int new_in_arena;
 };
 
 __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
@@ -90,7 +86,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
   // every scalar this CTA needs goes out in ONE round trip (len, position, keep flag), and the cos/sin row that depends on the
   // position right behind it, so that the front end below costs two dependent L2 round trips instead of four
   const bool fused = fz.partial != nullptr;
-  const int len = kv_len[b] + fz.new_in_arena;
+  const int len = kv_len[b];
   const int pos_b = fused ? fz.pos[b] : 0;
   const bool persist = fused && (fz.keep == nullptr || fz.keep[b] != 0);
   int kps = (len + n_split - 1) / n_split;
@@ -338,7 +334,7 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
     if (quirk_pad && split == 0) {
       int mx = 0;
       for (int i = 0; i < B; ++i) mx = max(mx, kv_len[i]);
-      n_pad = mx - (len - fz.new_in_arena);
+      n_pad = mx - len;
       if (n_pad > 0) M = fmaxf(M, 0.f);
     }
     float L = 0.f, O = 0.f;
@@ -361,11 +357,6 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
         ws_ml[slot * 2 + 1] = L;
       }
     }
-  }
-  // a token that is not kept leaves its slot: the CTA whose key range ended with it (every tile of it has been consumed above)
-  if (fz.new_in_arena && fz.keep != nullptr && threadIdx.x < 32 && n_keys > 0 && k1 == len && fz.keep[b] == 0) {
-    bf16* row = (threadIdx.x < 16 ? fz.k_arena_w : fz.v_arena_w) + (((int64_t)b * heads + h) * cap + (len - 1)) * AD_HD;
-    *reinterpret_cast<uint4*>(row + (threadIdx.x & 15) * 8) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -405,7 +396,6 @@ extern "C" int dl_attn_decode(const void* q, int q_row_stride, const void* k_are
   float* ws_acc = (float*)workspace;
   float* ws_ml = ws_acc ? ws_acc + (int64_t)B * heads * n_split * AD_HD : nullptr;
   AdFused fz = {};
-  fz.new_in_arena = 0;
   dl_launch_pdl(attn_decode_kernel, dim3(heads, B, n_split), dim3(AD_THREADS), sizeof(AdSmem), stream, (const bf16*)q, q_row_stride,
                 (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)k_side, (const bf16*)v_side, kv_len, (bf16*)out, ws_acc, ws_ml,
                 B, heads, cap, n_split, scale, quirk_pad, fz);
@@ -444,7 +434,6 @@ extern "C" int dl_attn_decode_fused(const float* qkv_partial, int n_slices, cons
   fz.l2_prefetch = (const uint8_t*)l2_prefetch;
   fz.l2_prefetch_bytes = l2_prefetch_bytes;
   fz.len_floor = len_floor > 0 ? len_floor : 0;
-  fz.new_in_arena = 0;
   dl_launch_pdl(attn_decode_kernel, dim3(heads, B, n_split), dim3(AD_THREADS), sizeof(AdSmem), stream, (const bf16*)nullptr, 0,
                 (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)nullptr, (const bf16*)nullptr, kv_len, (bf16*)out, ws_acc, ws_ml,
                 B, heads, cap, n_split, scale, quirk_pad, fz);
@@ -454,31 +443,3 @@ extern "C" int dl_attn_decode_fused(const float* qkv_partial, int n_slices, cons
   DL_CHECK_LAUNCH("dl_attn_decode_fused");
 }
 
-// Decode step with dec_gemm.cu's QKV epilogue: q [B, heads*128] rotated (unscaled), the new token's k / v already at slot kv_len[b].
-extern "C" int dl_attn_decode_inplace(const void* q, int q_row_stride, void* k_arena, void* v_arena, const int32_t* kv_len,
-                                      const uint8_t* keep, void* out, void* workspace, int B, int heads, int head_dim, int cap,
-                                      int n_split, float scale, int quirk_pad, int len_floor, cudaStream_t stream) {
-  DL_REQUIRE(head_dim == AD_HD && n_split >= 1 && (n_split == 1 || workspace != nullptr) && q != nullptr, "dl_attn_decode_inplace");
-  if (B == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AdSmem));
-    if (e != cudaSuccess) return dl_set_error((int)e, "dl_attn_decode_inplace(smem attr)");
-    attr_set = true;
-  }
-  float* ws_acc = (float*)workspace;
-  float* ws_ml = ws_acc ? ws_acc + (int64_t)B * heads * n_split * AD_HD : nullptr;
-  AdFused fz = {};
-  fz.keep = keep;
-  fz.k_arena_w = (bf16*)k_arena;
-  fz.v_arena_w = (bf16*)v_arena;
-  fz.len_floor = len_floor > 0 ? len_floor : 0;
-  fz.new_in_arena = 1;
-  dl_launch_pdl(attn_decode_kernel, dim3(heads, B, n_split), dim3(AD_THREADS), sizeof(AdSmem), stream, (const bf16*)q, q_row_stride,
-                (const bf16*)k_arena, (const bf16*)v_arena, (const bf16*)nullptr, (const bf16*)nullptr, kv_len, (bf16*)out, ws_acc, ws_ml,
-                B, heads, cap, n_split, scale, quirk_pad, fz);
-  if (n_split > 1)
-    dl_launch_pdl(attn_decode_combine_kernel, dim3(heads, B), dim3(AD_HD), 0, stream, (const float*)ws_acc, (const float*)ws_ml,
-                  (bf16*)out, heads, n_split);
-  DL_CHECK_LAUNCH("dl_attn_decode_inplace");
-}

@@ -54,8 +54,6 @@ class Session:
         self.tokens = torch.zeros(B, max(max_new, 1), device=dev, dtype=torch.int64)
         self.finished = torch.zeros(B, device=dev, dtype=torch.int32)
         self.partial = e(eng.max_partial_elems(B), dtype=torch.float32)
-        # partial sums of squares of the residual rows, left by each producer of the fused decode chain for the next RMSNorm-on-load
-        self.ssq = e(B * max(eng.L.dec_gemm_residual_parts(H, H), eng.L.dec_gemm_residual_parts(H, I), 1), dtype=torch.float32)
         D = c.sparse_config["d_model"]
         self.tp_ln = e(B, H)
         self.tp_logits = e(B, 2)
@@ -101,7 +99,6 @@ class Engine:
         self.packed_attn = os.environ.get("DLB200_PACKED_ATTN", "tc")  # CLIP / predictor attention: "tc" (tcgen05) | "mma"
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
-        self.decode_chain = os.environ.get("DLB200_DECODE_CHAIN", "v2")
         self.attn_early_kv = os.environ.get("DLB200_ATTN_EARLY_KV", "1") == "1"  # fetch prefill-time K/V tiles before the PDL wait
         self.attn_prefetch_wo = os.environ.get("DLB200_ATTN_PREFETCH_WO", "0") == "1"  # o_proj weight -> L2 during decode attention (measured: no gain)
         # stream-K workspace of dl_linear (parked partial accumulators + flags): zeroed once, used by the main stream's launches only
@@ -642,72 +639,7 @@ class Engine:
         return max(1, min(want, ub_len // 512, 16))
 
     def decode_layers(self, sess: Session, use_decisions: bool, quirk: bool):
-        """embed(next_ids) -> L decoder layers -> final norm -> lm_head: writes sess.logits (bf16 [B,V]).
-        Fused chain (csrc/dec_gemm.cu): per layer QKV (RMSNorm on load, cluster split-K reduce, RoPE, k/v written into the arena) ->
-        ragged attention -> O (+ residual + sum of squares) -> gate|up (RMSNorm on load, SwiGLU) -> down (+ residual + sum of squares)."""
-        if self.decode_chain == "v1":
-            return self.decode_layers_v1(sess, use_decisions, quirk)
-        c, sc = self.cfg, self.cfg.sparse_config
-        m = self.model.model
-        L_ = self.L
-        B, H, I, V = sess.B, c.hidden_size, c.intermediate_size, c.vocab_size
-        nh = c.num_attention_heads
-        hd = H // nh
-        SL, Lyr, eps = sc["sparse_layer"], c.num_hidden_layers, c.rms_norm_eps
-        a = sess.arena
-        st = _stream()
-        pk = self.packed
-        scale = 1.0 / math.sqrt(hd)
-        parts_o, parts_d = L_.dec_gemm_residual_parts(H, H), L_.dec_gemm_residual_parts(H, I)
-        L_.embed_rows_ssq(_p(sess.next_ids), _p(m.embed_tokens.weight), _p(sess.xres), _p(sess.ssq), B, H, st)
-        self.launches += 1
-        parts = 1
-        keep = None
-        join_side = False
-        for l in range(Lyr):
-            W = pk["layers"][l]
-            if l == SL and use_decisions:
-                tp = m.output_text_score_predictor.output_mlp
-                D = tp[1].weight.shape[0]
-                # the predictor only needs this layer's INPUT (the residual stream) and its decision is first consumed by this layer's
-                # attention kernel: it runs on a side stream next to the layer's QKV GEMM
-                cur = torch.cuda.current_stream()
-                side = self.side_stream
-                side.wait_stream(cur)
-                sst = ctypes.c_void_p(side.cuda_stream)
-                s_tp = L_.skinny_gemm_splits(D, H, self.skinny_target_ctas)
-                L_.layernorm(_p(sess.xres), _p(tp[0].weight), _p(tp[0].bias), _p(sess.tp_ln), B, H, tp[0].eps, sst)
-                L_.skinny_gemm(_p(sess.tp_ln), _p(tp[1].weight), _p(sess.tp_partial), B, D, H, s_tp, self.l2_prefetch_mb, sst)
-                L_.text_decision(_p(sess.tp_partial), s_tp, B, D, _p(tp[1].bias), _p(tp[3].weight), _p(tp[3].bias), _p(tp[5].weight),
-                                 _p(tp[5].bias), _p(tp[7].weight), _p(tp[7].bias), _p(sess.forced), _p(a.step), -1, _p(a.keep),
-                                 _p(sess.tp_logits), sst)
-                self.launches += 3
-                keep = a.keep
-                join_side = True
-            K_, V_, cap = a.layer(l)
-            kvl = a.kv_len[l]
-            L_.dec_gemm_qkv(_p(sess.xres), _p(sess.ssq), parts, _p(W["ln1"]), eps, _p(W["wqkv"]), _p(sess.q), _p(K_), _p(V_), _p(kvl),
-                            _p(a.pos), _p(pk["cos"]), _p(pk["sin"]), B, nh, hd, cap, H, st)
-            ns = self._n_split(B, nh, cap)
-            if ns > 1 and sess.attn_ws is None:
-                sess.attn_ws = torch.empty(L_.attn_decode_workspace_bytes(B, nh, 16) // 4, device=self.device, dtype=torch.float32)
-            if join_side:  # the keep decision decides whether the new token's slot survives this layer's attention kernel
-                torch.cuda.current_stream().wait_stream(self.side_stream)
-                join_side = False
-            L_.attn_decode_inplace(_p(sess.q), H, _p(K_), _p(V_), _p(kvl), _p(keep if l >= SL else None), _p(sess.attn), _p(sess.attn_ws),
-                                   B, nh, hd, cap, ns, scale, 1 if (quirk and l >= SL and (keep is not None or not a.hi_exact)) else 0,
-                                   (a.floor_lo if l < SL else a.floor_hi) if self.attn_early_kv else 0, st)
-            L_.dec_gemm_residual(_p(sess.attn), _p(W["wo"]), _p(sess.xres), _p(sess.ssq), B, H, H, st)
-            L_.dec_gemm_swiglu(_p(sess.xres), _p(sess.ssq), parts_o, _p(W["ln2"]), eps, _p(W["wgu"]), _p(sess.act), B, I, H, st)
-            L_.dec_gemm_residual(_p(sess.act), _p(W["wd"]), _p(sess.xres), _p(sess.ssq), B, H, I, st)
-            parts = parts_d
-            self.launches += 5 + (1 if ns > 1 else 0)
-        L_.dec_gemm_logits(_p(sess.xres), _p(sess.ssq), parts, _p(m.norm.weight), eps, _p(self.model.lm_head.weight), _p(sess.logits), B, V, H, st)
-        self.launches += 1
-        return keep
-
-    def decode_layers_v1(self, sess: Session, use_decisions: bool, quirk: bool):
-        """round-1 chain (split-K slices through global memory, 7 launches per layer): kept behind DLB200_DECODE_CHAIN=v1 for A/B timing"""
+        """embed(next_ids) -> L decoder layers -> final norm -> lm_head: writes sess.logits (bf16 [B,V])."""
         c, sc = self.cfg, self.cfg.sparse_config
         m = self.model.model
         L_ = self.L

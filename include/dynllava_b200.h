@@ -182,32 +182,6 @@ int dl_text_decision(const float* partial, int splits, int B, int D, const void*
                      const void* w5, const void* b5, const void* w7, const void* b7, const uint8_t* forced,
                      const int32_t* step_counter, int forced_offset, uint8_t* keep, void* logits_out, cudaStream_t stream);
 
-/* ---- decode step, fused form (dec_gemm.cu): the small ops between two weight-streaming GEMMs live in the GEMMs' prologues / epilogues,
- * so a decoder layer at q_len == 1 is QKV -> attention -> O -> gate|up -> down (DML:1271-1305 with :134-139, :253-285, :328 folded in).
- * M = batch <= 64, K % 64 == 0.  `ssq` float [M, n_parts]: partial sums of squares of the rows of the bf16 residual stream x [M, K],
- * left by the previous producer (dl_embed_rows_ssq: 1 part; dl_dec_gemm_residual: dl_dec_gemm_residual_parts(N, K) parts). ---- */
-/* embed_tokens (DML:1725) + the row's sum of squares.  ids int64 [n] on device; ssq float [n]. */
-int dl_embed_rows_ssq(const int64_t* ids, const void* table, void* out, float* ssq, int n, int H, cudaStream_t stream);
-/* RMSNorm(x) on load -> q|k|v projection (split-K over a thread-block cluster, reduced through distributed shared memory) -> RoPE ->
- * q_out [M, heads*128] (rotated, unscaled), k / v written into the arenas [M, heads, cap, 128] at slot kv_len[m] (DML:1011-1083). */
-int dl_dec_gemm_qkv(const void* x, const float* ssq, int n_parts, const void* norm_w, float eps, const void* w_qkv, void* q_out,
-                    void* k_arena, void* v_arena, const int32_t* kv_len, const int32_t* pos, const void* cos_table,
-                    const void* sin_table, int M, int heads, int head_dim, int cap, int K, cudaStream_t stream);
-/* xres[M,N] = bf16(xres + bf16(x_in[M,K] . W[N,K]^T)) (cluster split-K) and ssq_out float [M, parts] for the next RMSNorm (DML:1289/:1295). */
-int dl_dec_gemm_residual(const void* x_in, const void* w, void* xres, float* ssq_out, int M, int N, int K, cudaStream_t stream);
-int dl_dec_gemm_residual_parts(int N, int K);
-/* RMSNorm(x) on load -> gate|up projection -> act_out [M,I] = bf16(bf16(silu(g)) * u) (DML:328).  w_gate_up [2I,K], I % 64 == 0. */
-int dl_dec_gemm_swiglu(const void* x, const float* ssq, int n_parts, const void* norm_w, float eps, const void* w_gate_up,
-                       void* act_out, int M, int I, int K, cudaStream_t stream);
-/* final RMSNorm(x) on load -> lm_head -> bf16 logits [M,N] (DML:2565, :2709). */
-int dl_dec_gemm_logits(const void* x, const float* ssq, int n_parts, const void* norm_w, float eps, const void* w, void* logits, int M,
-                       int N, int K, cudaStream_t stream);
-/* K3 for that chain: q [B, heads*128] as written by dl_dec_gemm_qkv; the new token is key kv_len[b] of the arena (already written);
- * keep uint8 [B] or NULL: a token that is not kept has its slot zeroed again after the attention (CU:153-241). */
-int dl_attn_decode_inplace(const void* q, int q_row_stride, void* k_arena, void* v_arena, const int32_t* kv_len, const uint8_t* keep,
-                           void* out, void* workspace, int B, int heads, int head_dim, int cap, int n_split, float scale,
-                           int quirk_pad, int len_floor, cudaStream_t stream);
-
 /* ---- greedy next token: transformers-4.37.2 greedy search step ------------------------------ */
 /* logits bf16 [B,V]; next_ids int64 [B]; tokens_out int64 [B,out_stride] slot step_counter[0] (NULL: skip);
  * finished int32 [B]; eos_token_id < 0 disables EOS tracking. */

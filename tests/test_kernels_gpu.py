@@ -1163,142 +1163,3 @@ def test_output_keep_index_first_call_duplicates_last_token(L):
     with pytest.raises(RuntimeError):
         L.output_keep_index(None, B, 4, 5, A, A + 5, None, P(rows), ST())  # n_keep > n
 
-
-# ---------------------------------------------------------------------------------------------- fused decode chain (dec_gemm.cu)
-def _split_parts(total, n_parts, seed):
-    """n_parts fp32 partials per row that sum (in fp32, any order within ~1e-7) to `total` [M]"""
-    g = torch.Generator().manual_seed(seed)
-    w = torch.rand(total.shape[0], n_parts, generator=g) + 0.1
-    return (w / w.sum(1, keepdim=True) * total[:, None]).float().contiguous()
-
-
-@pytest.mark.parametrize("M,N,K", [(8, 4096, 4096), (8, 4096, 11008), (5, 512, 1024), (16, 5120, 5120), (33, 1024, 512), (1, 256, 256)])
-def test_dec_gemm_residual_cluster_reduce(L, M, N, K):
-    """O / down projection of the decode step: split-K over a thread-block cluster, x = bf16(x + bf16(sum)) and the sum of squares"""
-    xin, w, x0 = rnd(M, K, seed=300), rnd(N, K, seed=301, scale=0.05), rnd(M, N, seed=302)
-    xres = x0.to(DEV).clone()
-    parts = L.dec_gemm_residual_parts(N, K)
-    ssq = torch.full((M, parts), float("nan"), device=DEV, dtype=torch.float32)
-    L.dec_gemm_residual(P(xin), P(w), P(xres), P(ssq), M, N, K, ST())
-    torch.cuda.synchronize()
-    proj = (xin.float() @ w.float().T).to(BF).float()
-    ref = (x0.float() + proj).to(BF).float()
-    got_x = xres.float().cpu()
-    # the fp32 summation order may flip the projection's bf16 rounding by one ulp; where x + proj cancels that ulp is several ulps of
-    # the (small) sum: bound the deviation by one ulp of the larger operand
-    assert ((got_x - ref).abs() <= 2 ** -6 * (x0.float().abs() + proj.abs()) + 1e-6).all()
-    assert (got_x != ref).float().mean().item() < 0.02
-    want = (xres.float().cpu() ** 2).sum(1)
-    got = ssq.cpu().sum(1)
-    assert torch.isfinite(got).all() and ((got - want).abs() <= 1e-4 * want).all(), (got, want)
-    # deterministic: same launch again on the updated residual of a fresh copy
-    xres2 = x0.to(DEV).clone()
-    ssq2 = torch.empty_like(ssq)
-    L.dec_gemm_residual(P(xin), P(w), P(xres2), P(ssq2), M, N, K, ST())
-    torch.cuda.synchronize()
-    assert torch.equal(xres, xres2) and torch.equal(ssq, ssq2)
-
-
-@pytest.mark.parametrize("M,heads,K,n_parts", [(8, 32, 4096, 256), (8, 32, 4096, 1), (3, 4, 512, 7), (16, 8, 1024, 32), (24, 4, 512, 3)])
-def test_dec_gemm_qkv_norm_on_load_rope_write(L, M, heads, K, n_parts):
-    """RMSNorm on load -> q|k|v -> RoPE -> q buffer + k / v rows at slot kv_len[m], against the oracle's rms_norm / apply_rope on the
-    bf16 projection (bit-exact except where the fp32 summation order flips a bf16 rounding)"""
-    hd, H, cap = 128, heads * 128, 40
-    x, lnw, w = rnd(M, K, seed=310), (1 + 0.1 * rnd(K, seed=311).float()).to(BF), rnd(3 * H, K, seed=312, scale=0.05)
-    ssq = _split_parts((x.float() ** 2).sum(1), n_parts, seed=313)
-    cos, sin = O.rope_tables(hd, 4096, 10000.0, BF)
-    g = torch.Generator().manual_seed(314)
-    pos = torch.randint(0, 4000, (M,), generator=g).to(torch.int32)
-    kvl = torch.randint(0, cap - 1, (M,), generator=g).to(torch.int32)
-    q = torch.full((M, H), float("nan"), device=DEV, dtype=BF)
-    Ka = torch.zeros(M, heads, cap, hd, device=DEV, dtype=BF)
-    Va = torch.zeros_like(Ka)
-    L.dec_gemm_qkv(P(x), P(ssq), n_parts, P(lnw), 1e-5, P(w), P(q), P(Ka), P(Va), P(kvl), P(pos), P(cos), P(sin), M, heads, hd, cap, K, ST())
-    torch.cuda.synchronize()
-    xn = O.rms_norm(x, lnw, 1e-5)
-    qkv = (xn.float() @ w.float().T).to(BF)
-    q4 = qkv[:, :H].view(M, 1, heads, hd).transpose(1, 2)
-    k4 = qkv[:, H:2 * H].view(M, 1, heads, hd).transpose(1, 2)
-    v4 = qkv[:, 2 * H:].view(M, heads, hd)
-    qr, kr = O.apply_rope(q4, k4, cos, sin, pos.long().view(M, 1))
-    # rounding flips of the projection (fp32 order) propagate through the rotation: compare within 2 bf16 ulps of the operand scale
-    def close(a, b):
-        a, b = a.float().cpu(), b.float()
-        assert (a - b).abs().max() <= 2 ** -6 * max(1.0, b.abs().max().item()), (a - b).abs().max()
-        assert ((a - b).abs() > 0).float().mean() < 0.05
-    close(q, qr[:, :, 0].reshape(M, H))
-    for m in range(M):
-        close(Ka[m, :, kvl[m]], kr[m, :, 0])
-        close(Va[m, :, kvl[m]], v4[m])
-        other = torch.ones(cap, dtype=torch.bool)
-        other[kvl[m]] = False
-        assert (Ka[m][:, other.to(DEV)] == 0).all() and (Va[m][:, other.to(DEV)] == 0).all()  # only the slot is written
-
-
-@pytest.mark.parametrize("M,I,K,n_parts", [(8, 11008, 4096, 256), (4, 512, 256, 1), (16, 1024, 512, 16)])
-def test_dec_gemm_swiglu_and_logits_norm_on_load(L, M, I, K, n_parts):
-    x, lnw, w = rnd(M, K, seed=320), (1 + 0.1 * rnd(K, seed=321).float()).to(BF), rnd(2 * I, K, seed=322, scale=0.05)
-    ssq = _split_parts((x.float() ** 2).sum(1), n_parts, seed=323)
-    xn = O.rms_norm(x, lnw, 1e-5)
-    act = torch.full((M, I), float("nan"), device=DEV, dtype=BF)
-    L.dec_gemm_swiglu(P(x), P(ssq), n_parts, P(lnw), 1e-5, P(w), P(act), M, I, K, ST())
-    # the same through the unfused round-1 kernels on the oracle's normalised rows: bit-identical when rstd rounds the same way
-    act_ref = torch.empty(M, I, device=DEV, dtype=BF)
-    L.skinny_gemm_swiglu(P(xn), P(w), P(act_ref), M, I, K, ST())
-    logits = torch.full((M, 2 * I), float("nan"), device=DEV, dtype=BF)
-    L.dec_gemm_logits(P(x), P(ssq), n_parts, P(lnw), 1e-5, P(w), P(logits), M, 2 * I, K, ST())
-    torch.cuda.synchronize()
-    da, dr = act.float(), act_ref.float()
-    assert torch.isfinite(da).all()
-    assert ((da - dr).abs() <= 0.03 * dr.abs() + 2e-3).all() and (da != dr).float().mean().item() < 0.02
-    want = (xn.float() @ w.float().T).to(BF)
-    ulp_close(logits, want, max_frac=0.02, abs_ok=2e-3)
-
-
-def test_embed_rows_ssq(L):
-    V, H, n = 50, 512, 6
-    table = rnd(V, H, seed=330)
-    ids = torch.tensor([3, 49, 0, 7, 7, 21], dtype=torch.int64)
-    out = torch.empty(n, H, device=DEV, dtype=BF)
-    ssq = torch.empty(n, device=DEV, dtype=torch.float32)
-    L.embed_rows_ssq(P(ids), P(table), P(out), P(ssq), n, H, ST())
-    torch.cuda.synchronize()
-    assert torch.equal(out.cpu(), table[ids])
-    want = (table[ids].float() ** 2).sum(1)
-    assert ((ssq.cpu() - want).abs() <= 1e-5 * want).all()
-
-
-@pytest.mark.parametrize("lens,n_split,quirk", [([146, 210, 64, 1], 1, 0), ([735, 650, 129, 300], 2, 0), ([40, 70, 70, 3], 1, 1), ([0, 5, 63, 64], 1, 0)])
-def test_attn_decode_inplace_equals_side_buffer_form(L, lens, n_split, quirk):
-    """the new token as key number kv_len[b] of the arena (written by the QKV GEMM epilogue) == the side-buffer form; a token that is not
-    kept leaves its slot zeroed, a kept one stays"""
-    B, nh, hd = len(lens), 4, 128
-    H = nh * hd
-    cap = max(lens) + 8
-    K = torch.zeros(B, nh, cap, hd, dtype=BF)
-    V = torch.zeros_like(K)
-    for b, n in enumerate(lens):
-        K[b, :, :n] = rnd(nh, n, hd, seed=340 + b)
-        V[b, :, :n] = rnd(nh, n, hd, seed=350 + b)
-    q, ks, vs = rnd(B, H, seed=360), rnd(B, nh, hd, seed=361), rnd(B, nh, hd, seed=362)
-    kvl = torch.tensor(lens, dtype=torch.int32, device=DEV)
-    keep = torch.tensor([1, 0, 1, 0], dtype=torch.uint8, device=DEV)
-    sc = 1.0 / math.sqrt(hd)
-    ws = torch.empty(max(L.attn_decode_workspace_bytes(B, nh, max(n_split, 1)) // 4, 1), device=DEV, dtype=torch.float32)
-    o1 = torch.empty(B, H, device=DEV, dtype=BF)
-    L.attn_decode(P(q), H, P(K.to(DEV)), P(V.to(DEV)), P(ks), P(vs), P(kvl), P(o1), P(ws), B, nh, hd, cap, n_split, sc, quirk, ST())
-    K2, V2 = K.to(DEV).clone(), V.to(DEV).clone()
-    for b, n in enumerate(lens):
-        K2[b, :, n] = ks[b].to(DEV)
-        V2[b, :, n] = vs[b].to(DEV)
-    o2 = torch.empty(B, H, device=DEV, dtype=BF)
-    L.attn_decode_inplace(P(q), H, P(K2), P(V2), P(kvl), P(keep), P(o2), P(ws), B, nh, hd, cap, n_split, sc, quirk, (min(lens) // 64) * 64, ST())
-    torch.cuda.synchronize()
-    # same keys, same math; the new token is merged as part of a tile instead of last, so the fp32 order differs slightly
-    assert (o1.float() - o2.float()).abs().max() <= 2 ** -7 * max(1.0, o1.float().abs().max().item())
-    for b, n in enumerate(lens):
-        if keep[b]:
-            assert torch.equal(K2[b, :, n].cpu(), ks[b]) and torch.equal(V2[b, :, n].cpu(), vs[b])
-        else:
-            assert (K2[b, :, n] == 0).all() and (V2[b, :, n] == 0).all()
-        assert torch.equal(K2[b, :, :n].cpu(), K[b, :, :n])
