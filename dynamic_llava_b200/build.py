@@ -23,8 +23,6 @@ SOURCES = [
     "rope_append.cu",
     "kv_turn.cu",
     "attn_decode.cu",
-    "attn_prefill_mma.cu",
-    "attn_prefill_tc2.cu",
     "attn_prefill_tc4.cu",
     "skinny_gemm.cu",
     "gemm2.cu",

@@ -1,5 +1,5 @@
 // K2 (v4): variable-length prefill attention — PERSISTENT tcgen05 pipeline.
-// Same contract as dl_attn_prefill_tc2 / dl_attn_packed_tc (attn_prefill_tc2.cu); reference op:
+// Contract: include/dynllava_b200.h (dl_attn_prefill_tc4 / dl_attn_packed_tc4); reference op:
 // F.scaled_dot_product_attention, llava/model/language_model/dynamic_modeling_llama.py:1114-1122 (causal, head_dim 128)
 // and custom_transformer_layer.py:153-180 / HF CLIPAttention (non-causal, head_dim 64).
 //

@@ -91,12 +91,9 @@ class Engine:
         if self.dtype != torch.bfloat16:
             raise RuntimeError("kernels compute in bf16: load the model with torch_dtype=torch.bfloat16")
         self.packed = None
-        # "tc4" (default: persistent tcgen05 kernel) | "tc2" (non-persistent tcgen05) | "mma" (warp-MMA tile path)
-        self.prefill_attn = os.environ.get("DLB200_PREFILL_ATTN", "tc4")
         self.side_stream = torch.cuda.Stream(device=self.device)  # text-predictor branch of the decode step
         self._cu_cache = {}
         self.attn_flags = int(os.environ.get("DLB200_ATTN_FLAGS", "0"))  # dl_attn_prefill_tc4 flags (bit 0: FMA-pipe exp2)
-        self.packed_attn = os.environ.get("DLB200_PACKED_ATTN", "tc")  # CLIP / predictor attention: "tc" (tcgen05) | "mma"
         self.skinny_target_ctas = int(os.environ.get("DLB200_SKINNY_CTAS", "296"))
         self.l2_prefetch_mb = int(os.environ.get("DLB200_L2_PREFETCH_MB", "-1"))
         self.attn_early_kv = os.environ.get("DLB200_ATTN_EARLY_KV", "1") == "1"  # fetch prefill-time K/V tiles before the PDL wait
@@ -253,18 +250,10 @@ class Engine:
         cu = self._cu_cache.get((B, N))  # one CSR header per shape, not one arange launch per attention call (57 per prefill)
         if cu is None:
             cu = self._cu_cache[(B, N)] = torch.arange(0, (B + 1) * N, N, device=qkv.device, dtype=torch.int32)
-        if hd == 64 and not causal and self.packed_attn == "tc":
-            if self.prefill_attn == "tc4":
-                self.L.attn_packed_tc4(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), self.attn_flags, _stream())
-            else:
-                self.L.attn_packed_tc(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), _stream())
-            self.launches += 1
-            return out
-        es = qkv.element_size()
-        k = ctypes.c_void_p(qkv.data_ptr() + C * es)
-        v = ctypes.c_void_p(qkv.data_ptr() + 2 * C * es)
-        self.L.attn_varlen(_p(qkv), 3 * C, hd, k, v, 0, hd, 3 * C, 1, _p(out), C, _p(cu), None, B, heads, hd, N,
-                           1 if causal else 0, 1.0 / math.sqrt(hd), _stream())
+        if hd != 64 or causal:
+            raise NotImplementedError("packed attention runs on the tcgen05 kernel for head_dim 64, non-causal (CLIP ViT-L/14, the predictor "
+                                      "blocks of the released checkpoints: d_model 512 / nhead 8)")
+        self.L.attn_packed_tc4(_p(qkv), _p(out), _p(cu), B * N, B, heads, hd, N, 1.0 / math.sqrt(hd), self.attn_flags, _stream())
         self.launches += 1
         return out
 
@@ -437,14 +426,7 @@ class Engine:
                            None, None, N, B, nh, hd, cap, _stream())
         attn = torch.empty(N, H, device=x.device, dtype=x.dtype)
         scale = 1.0 / math.sqrt(hd)
-        if self.prefill_attn == "tc4":
-            self.L.attn_prefill_tc4(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, self.attn_flags,
-                                    _stream())
-        elif self.prefill_attn == "tc2":
-            self.L.attn_prefill_tc2(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, _stream())
-        else:
-            self.L.attn_varlen(_p(qkv), 3 * H, hd, _p(K), _p(V), nh * cap * hd, cap * hd, hd, 0, _p(attn), H, _p(cu), _p(kvl), B, nh,
-                               hd, Lq, 1, scale, _stream())
+        self.L.attn_prefill_tc4(_p(qkv), 3 * H, _p(K), _p(V), _p(attn), H, _p(cu), _p(kvl), N, B, nh, cap, Lq, scale, self.attn_flags, _stream())
         self.launches += 2
         self.linear(attn, W["wo"], residual=x, out=x)  # x + o_proj(attn): bf16 projection, bf16 add, in the GEMM epilogue (:1289)
         xn = self.rmsnorm(x, W["ln2"], c.rms_norm_eps, out=xn)

@@ -171,6 +171,20 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             raise RuntimeError(f"state_dict mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
         return model
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *model_args, config=None, torch_dtype=None, dtype=None, device_map=None,
+                        low_cpu_mem_usage=None, **kwargs):
+        """`DynamicLlavaLlamaForCausalLM.from_pretrained(path, low_cpu_mem_usage=True, device_map="auto", torch_dtype=...)` as the
+        reference's builder calls it (dynamic_llava_builder.py:191-193), also reached through `AutoModelForCausalLM.from_pretrained`
+        once `register_auto_classes()` ran (dynamic_llava_llama.py:172-173).  Local HF-format directories only (no hub access)."""
+        from .builder import load_model_from_dir
+        dev = "cuda"
+        if isinstance(device_map, (str, torch.device)) and str(device_map) not in ("auto", "balanced", "sequential"):
+            dev = device_map
+        elif isinstance(device_map, dict):
+            raise NotImplementedError("per-module device maps (accelerate layer placement) are out of scope: one replica per GPU")
+        return load_model_from_dir(str(pretrained_model_name_or_path), device=dev, torch_dtype=torch_dtype if torch_dtype is not None else dtype)
+
     # ---- engine plumbing ---------------------------------------------------------------------------------------
     @property
     def engine(self) -> Engine:
@@ -477,6 +491,22 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         if image_sizes is not None:
             model_inputs["image_sizes"] = image_sizes
         return model_inputs
+
+
+def register_auto_classes():
+    """`AutoConfig.register("dynamic_llava_llama", DynamicLlavaConfig)` / `AutoModelForCausalLM.register(DynamicLlavaConfig,
+    DynamicLlavaLlamaForCausalLM)` (dynamic_llava_llama.py:172-173).  The Auto machinery wants a `PretrainedConfig` subclass; ours is a
+    plain attribute bag, so a same-named thin PretrainedConfig carries the parsed config.json and the model class re-reads the
+    directory in `from_pretrained`.  Called on import of `llava.model` (as the reference registers at import time)."""
+    from transformers import AutoConfig, AutoModelForCausalLM, PretrainedConfig
+
+    class _HFConfig(PretrainedConfig):
+        model_type = "dynamic_llava_llama"
+
+    _HFConfig.__name__ = _HFConfig.__qualname__ = "DynamicLlavaConfig"
+    AutoConfig.register("dynamic_llava_llama", _HFConfig, exist_ok=True)
+    AutoModelForCausalLM.register(_HFConfig, DynamicLlavaLlamaForCausalLM, exist_ok=True)
+    return _HFConfig
 
 
 # Export-name alias only: the dense baseline class name that llava/model/__init__.py:2 also exports.

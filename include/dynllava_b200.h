@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define DL_B200_ABI_VERSION 5  /* 5: dl_linear / dl_linear_swiglu (2-CTA tcgen05 GEMM) replace dl_gemm_bias_act; 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points;
+#define DL_B200_ABI_VERSION 6  /* 6: superseded attention kernels (warp-MMA dl_attn_varlen, non-persistent dl_attn_prefill_tc2 / dl_attn_packed_tc) removed; 5: dl_linear / dl_linear_swiglu (2-CTA tcgen05 GEMM) replace dl_gemm_bias_act; 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points;
                                  * 4: no-KV-cache output sparsification (dl_output_rank / dl_output_keep_index) */
 
 int dl_version(void);
@@ -128,31 +128,17 @@ int dl_attn_decode_fused(const float* qkv_partial, int n_slices, const int32_t* 
  * len_floor: host-known lower bound of every kv_len[b] (the prefill length; 0 = unknown): K/V tiles below it are fetched
  * before the kernel waits on its predecessor. */
 
-/* ---- K2/K6/K7: variable-length attention (warp-MMA tile path), DML:1114-1122; CTL:164-169; HF CLIPAttention ---- */
-/* Addresses: Q(b,i,h) = q + (cu_q[b]+i)*q_tok_stride + h*q_head_stride;
- * K(b,j,h) = k + b*kv_batch_stride + h*kv_head_stride + ((kv_packed ? cu_q[b] : 0) + j)*kv_tok_stride (V alike);
- * O(b,i,h) = out + (cu_q[b]+i)*o_tok_stride + h*head_dim.  kv_past int32 [B] or NULL: keys already cached before this
- * pass (query i attends keys j <= i + kv_past[b] when causal). head_dim 64 or 128. */
-int dl_attn_varlen(const void* q, int64_t q_tok_stride, int64_t q_head_stride, const void* k, const void* v,
-                   int64_t kv_batch_stride, int64_t kv_head_stride, int64_t kv_tok_stride, int kv_packed, void* out,
-                   int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int B, int heads, int head_dim,
-                   int max_q_len, int causal, float scale, cudaStream_t stream);
-/* K2 (v2, kept as the simple non-persistent form): TMA + tcgen05/TMEM causal prefill attention, head_dim 128, K/V in the arena;
- * 256 query rows per CTA, ping-pong softmax groups, P and O resident in TMEM (attn_prefill_tc2.cu). */
-int dl_attn_prefill_tc2(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
-                        int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
-                        int cap, int max_q_len, float scale, cudaStream_t stream);
-
-/* K6/K7 on the same tcgen05 pipeline: non-causal attention, head_dim 64, q|k|v packed in one fused projection buffer
- * qkv [n_tok, 3*heads*64]; per-sample ranges from cu_q; out [n_tok, heads*64].  HF CLIPAttention (CLIP ViT-L/14) and the
- * VisionPredictor blocks (CTL:153-180). */
-int dl_attn_packed_tc(const void* qkv, void* out, const int32_t* cu_q, int n_tok, int B, int heads, int head_dim,
-                      int max_q_len, float scale, cudaStream_t stream);
-
-/* K2 v4 / K6-K7 v4 (default): same contracts as dl_attn_prefill_tc2 / dl_attn_packed_tc.  64-key half tiles with double-buffered
- * S in TMEM, one MMA issuer per softmax group, in a persistent kernel (grid = #SMs, heaviest-first tile list, barriers indexed by
- * running counters so that the loads and S(0)/S(1) of the next tile hide under the current tile's tail), O written with TMA stores
- * (attn_prefill_tc4.cu).  flags bit 0: one exp2 in four on the FMA pipe (degree-3 polynomial, rel. error 7.5e-5) instead of the SFU. */
+/* ---- K2 / K6 / K7: prefill attention on the persistent TMA + tcgen05 pipeline (attn_prefill_tc4.cu), DML:1114-1122; CTL:164-169; HF
+ * CLIPAttention.
+ * dl_attn_prefill_tc4: causal, head_dim 128.  q [n_tok, heads*128] rows at q_tok_stride elements (the fused q|k|v projection);
+ * K / V in the arena [B, heads, cap, 128] (this pass's keys already appended); per-sample query ranges from cu_q int32 [B+1];
+ * kv_past int32 [B] or NULL: keys cached before this pass (query i attends keys j <= i + kv_past[b]); out [n_tok, heads*128] rows at
+ * o_tok_stride elements.
+ * dl_attn_packed_tc4: non-causal, head_dim 64, q|k|v packed in one fused projection buffer qkv [n_tok, 3*heads*64]; out [n_tok, heads*64]
+ * (CLIP ViT-L/14, the VisionPredictor blocks CTL:153-180).
+ * 64-key half tiles with double-buffered S in TMEM, one MMA issuer per softmax group, grid = #SMs, heaviest-first tile list, barriers
+ * indexed by running counters so that the loads and S(0)/S(1) of the next tile hide under the current tile's tail, O written with TMA
+ * stores.  flags bit 0: one exp2 in four on the FMA pipe (degree-3 polynomial, rel. error 7.5e-5) instead of the SFU. */
 int dl_attn_prefill_tc4(const void* q, int64_t q_tok_stride, const void* k_arena, const void* v_arena, void* out,
                         int64_t o_tok_stride, const int32_t* cu_q, const int32_t* kv_past, int n_tok, int B, int heads,
                         int cap, int max_q_len, float scale, int flags, cudaStream_t stream);

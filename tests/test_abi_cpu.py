@@ -22,7 +22,7 @@ def test_library_builds_and_loads(so_path):
     assert os.path.exists(so_path)
     dll = ctypes.CDLL(so_path)
     dll.dl_version.restype = ctypes.c_int
-    assert dll.dl_version() == 5
+    assert dll.dl_version() == 6
     dll.dl_last_error_string.restype = ctypes.c_char_p
     assert isinstance(dll.dl_last_error_string(), bytes)
 

@@ -357,3 +357,40 @@ def test_eval_driver_import_surface():
             "print('ok')")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)  # own process: it patches torch.nn
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-1500:]
+
+
+def test_auto_classes_registered_and_from_pretrained(tmp_path):
+    """the reference registers its classes with transformers' Auto factories at import time (dynamic_llava_llama.py:172-173) and its
+    builder loads through `DynamicLlavaLlamaForCausalLM.from_pretrained(path, low_cpu_mem_usage=True, torch_dtype=float16, ...)`
+    (dynamic_llava_builder.py:62, :191-193): both entry points exist here and return the same weights; float16 is served in bf16 with a
+    warning, anything else is refused"""
+    import json
+    from safetensors.torch import save_file
+    from transformers import AutoConfig, AutoModelForCausalLM
+    import llava.model  # noqa: F401  (registration happens on import)
+    from llava.model import DynamicLlavaLlamaForCausalLM
+    cfg = preset("toy")
+    cfg["sparse_config"]["use_output_text_predictor"] = True
+    sd = {k: v.to(torch.bfloat16).contiguous() for k, v in numpy_state_dict(cfg, 0).items()}
+    ck = tmp_path / "ck"
+    ck.mkdir()
+    cj = {k: v for k, v in cfg.items() if k != "vision"}
+    cj.update(model_type="dynamic_llava_llama", mm_vision_tower=str(tmp_path / "clip"), mm_projector_type="mlp2x_gelu", architectures=["DynamicLlavaLlamaForCausalLM"])
+    json.dump(cj, open(ck / "config.json", "w"))
+    (tmp_path / "clip").mkdir()
+    vc = dict(cfg["vision"], model_type="clip_vision_model")
+    json.dump(vc, open(tmp_path / "clip" / "config.json", "w"))
+    save_file(sd, str(ck / "model.safetensors"))
+    hf_cfg = AutoConfig.from_pretrained(str(ck))
+    assert hf_cfg.model_type == "dynamic_llava_llama" and type(hf_cfg).__name__ == "DynamicLlavaConfig"
+    assert hf_cfg.sparse_config["sparse_layer"] == cfg["sparse_config"]["sparse_layer"]
+    m1 = AutoModelForCausalLM.from_pretrained(str(ck), device_map="cpu")
+    assert isinstance(m1, DynamicLlavaLlamaForCausalLM)
+    with pytest.warns(UserWarning, match="float16"):
+        m2 = DynamicLlavaLlamaForCausalLM.from_pretrained(str(ck), low_cpu_mem_usage=True, device_map="cpu", torch_dtype=torch.float16)
+    for m in (m1, m2):
+        got = m.state_dict()
+        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+        assert m.dtype == torch.bfloat16 and m.config.sparse_config == cfg["sparse_config"]
+    with pytest.raises(NotImplementedError, match="bfloat16 only"):
+        DynamicLlavaLlamaForCausalLM.from_pretrained(str(ck), device_map="cpu", torch_dtype=torch.float32)

@@ -110,8 +110,9 @@ def bench_attn_prefill(out):
         past = torch.zeros(B, device=DEV, dtype=torch.int32)
         flop = 2.0 * Lq * Lq * H * B  # causal: 4*L*L*H/2 per sample
         sc = 1.0 / math.sqrt(hd)
-        ms_tc2 = timeit(lambda i: L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, sc, ST()), 1)
-        o_tc = o.clone()  # reference for the max-diff columns
+        q4 = qkv[:, :H].view(B, Lq, nh, hd).transpose(1, 2)
+        k4, v4 = K[:, :, :Lq], V[:, :, :Lq]
+        o_ref = F.scaled_dot_product_attention(q4, k4, v4, is_causal=True).transpose(1, 2).reshape(N, H)  # library result for the max-diff columns
         t3 = {}
         for fl in (0, 1):
             for nm, fn3 in (("tc4", L.attn_prefill_tc4),):
@@ -119,16 +120,9 @@ def bench_attn_prefill(out):
                 t3[f"{nm}_f{fl}_us"] = ms3 * 1e3
                 t3[f"{nm}_f{fl}_TFLOPs"] = flop / ms3 / 1e9
                 t3[f"{nm}_f{fl}_frac_of_sustained_bf16"] = flop / ms3 / 1e9 / pk["bf16_tflops_sustained"]
-                t3[f"{nm}_f{fl}_vs_tc2_maxdiff"] = (o.float() - o_tc.float()).abs().max().item()
-        ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * H, hd, P(K), P(V), nh * cap * hd, cap * hd, hd, 0, P(o), H, P(cu), P(past), B, nh, hd, Lq, 1, sc, ST()), 1)
-        diff = (o.float() - o_tc.float()).abs().max().item()
-        q4 = qkv[:, :H].view(B, Lq, nh, hd).transpose(1, 2)
-        k4, v4 = K[:, :, :Lq], V[:, :, :Lq]
+                t3[f"{nm}_f{fl}_vs_sdpa_maxdiff"] = (o.float() - o_ref.float()).abs().max().item()
         ms_sdpa = timeit(lambda i: F.scaled_dot_product_attention(q4, k4, v4, is_causal=True), 1)
-        rows.append({"case": name, "GFLOP": flop / 1e9, "mma_us": ms_mma * 1e3,
-                     "mma_TFLOPs": flop / ms_mma / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "torch_sdpa_TFLOPs": flop / ms_sdpa / 1e9,
-                     "tc2_vs_mma_maxdiff": diff, "tc2_us": ms_tc2 * 1e3, "tc2_TFLOPs": flop / ms_tc2 / 1e9,
-                     "tc2_frac_of_sustained_bf16": flop / ms_tc2 / 1e9 / pk["bf16_tflops_sustained"], **t3})
+        rows.append({"case": name, "GFLOP": flop / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "torch_sdpa_TFLOPs": flop / ms_sdpa / 1e9, **t3})
         print("ATTN_PREFILL", rows[-1], flush=True)
     out["attn_prefill"] = rows
     rows = []
@@ -139,22 +133,17 @@ def bench_attn_prefill(out):
         cu = torch.arange(0, (B + 1) * N, N, device=DEV, dtype=torch.int32)
         flop = 4.0 * N * N * C * B
         sc = 1.0 / math.sqrt(hd)
-        ms_tc = timeit(lambda i: L.attn_packed_tc(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, ST()), 1)
-        o1 = o.clone()
+        q4 = qkv.view(B, N, 3, nh, hd).permute(2, 0, 3, 1, 4)
+        o1 = F.scaled_dot_product_attention(q4[0], q4[1], q4[2]).transpose(1, 2).reshape(B * N, C)
         t3 = {}
         for fl in (0, 1):
             for nm, fn3 in (("tc4", L.attn_packed_tc4),):
                 ms3 = timeit(lambda i: fn3(P(qkv), P(o), P(cu), B * N, B, nh, hd, N, sc, fl, ST()), 1)
                 t3[f"{nm}_f{fl}_us"] = ms3 * 1e3
                 t3[f"{nm}_f{fl}_TFLOPs"] = flop / ms3 / 1e9
-                t3[f"{nm}_f{fl}_vs_tc2_maxdiff"] = (o.float() - o1.float()).abs().max().item()
-        kp = ctypes.c_void_p(qkv.data_ptr() + C * 2)
-        vp = ctypes.c_void_p(qkv.data_ptr() + 2 * C * 2)
-        ms_mma = timeit(lambda i: L.attn_varlen(P(qkv), 3 * C, hd, kp, vp, 0, hd, 3 * C, 1, P(o), C, P(cu), None, B, nh, hd, N, 0, sc, ST()), 1)
-        q4 = qkv.view(B, N, 3, nh, hd).permute(2, 0, 3, 1, 4)
+                t3[f"{nm}_f{fl}_vs_sdpa_maxdiff"] = (o.float() - o1.float()).abs().max().item()
         ms_sdpa = timeit(lambda i: F.scaled_dot_product_attention(q4[0], q4[1], q4[2]), 1)
-        rows.append({"case": name, "GFLOP": flop / 1e9, "tcgen05_us": ms_tc * 1e3, "tcgen05_TFLOPs": flop / ms_tc / 1e9, "mma_us": ms_mma * 1e3,
-                     "mma_TFLOPs": flop / ms_mma / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, "maxdiff_tc_vs_mma": (o.float() - o1.float()).abs().max().item(), **t3})
+        rows.append({"case": name, "GFLOP": flop / 1e9, "torch_sdpa_us": ms_sdpa * 1e3, **t3})
         print("ATTN_PACKED", rows[-1], flush=True)
     out["attn_packed_hd64"] = rows
 
@@ -217,24 +206,6 @@ def bench_skinny(out):
     out["skinny_gemm"] = rows
 
 
-def bench_gemm(out):
-    import torch.nn.functional as F
-    pk = peaks()
-    rows = []
-    for name, M, N, K in [("clip patch-embed B=8", 4608, 1024, 640), ("projector fc1 B=8", 4608, 4096, 1024), ("clip fc1 B=8", 4616, 4096, 1024),
-                          ("llama qkv prefill B=8", 4856, 12288, 4096)]:
-        x, w, b = torch.randn(M, K, device=DEV, dtype=BF), torch.randn(N, K, device=DEV, dtype=BF) * 0.05, torch.randn(N, device=DEV, dtype=BF)
-        o = torch.empty(M, N, device=DEV, dtype=BF)
-        ms = timeit(lambda i: L.gemm_bias_act(P(x), P(w), P(b), P(o), M, N, K, 0, ST()), 1)
-        ms_c = timeit(lambda i: F.linear(x, w, b), 1)
-        fl = 2.0 * M * N * K
-        rows.append({"case": name, "GFLOP": fl / 1e9, "tcgen05_tile_us": ms * 1e3, "tcgen05_tile_TFLOPs": fl / ms / 1e9,
-                     "frac_of_sustained_bf16": fl / ms / 1e9 / pk["bf16_tflops_sustained"], "cublaslt_us": ms_c * 1e3, "cublaslt_TFLOPs": fl / ms_c / 1e9,
-                     "maxdiff_vs_cublas": (o.float() - F.linear(x, w, b).float()).abs().max().item()})
-        print("GEMM", rows[-1], flush=True)
-    out["gemm_tc"] = rows
-
-
 def main():
     global L
     ap = argparse.ArgumentParser()
@@ -252,8 +223,7 @@ def main():
         bench_attn_decode(out)
     if "skinny" in todo:
         bench_skinny(out)
-    if "gemm" in todo:
-        bench_gemm(out)
+    # dense GEMMs: tools/bench_linear.py
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(out, open(a.out, "w"), indent=1)
 

@@ -1,4 +1,4 @@
-"""Launch the prefill attention kernels a few times on one shape (for `ncu --set full -k regex:attn_prefill_tc`; KERNEL=tc2|tc4, FLAGS, B, NH, LQ, REPS from the environment)."""
+"""Launch the prefill attention kernels a few times on one shape (for `ncu --set full -k regex:attn_prefill_tc`; FLAGS, B, NH, LQ, REPS from the environment)."""
 import ctypes
 import math
 import os
@@ -23,11 +23,7 @@ V = torch.randn(B, nh, cap, hd, device="cuda", dtype=torch.bfloat16)
 o = torch.empty(N, H, device="cuda", dtype=torch.bfloat16)
 cu = torch.arange(0, (B + 1) * Lq, Lq, device="cuda", dtype=torch.int32)
 past = torch.zeros(B, device="cuda", dtype=torch.int32)
-which = os.environ.get("KERNEL", "tc4")
 for _ in range(int(os.environ.get("REPS", 4))):
-    if which == "tc2":
-        L.attn_prefill_tc2(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), ST())
-    else:
-        L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), int(os.environ.get("FLAGS", 0)), ST())
+    L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), int(os.environ.get("FLAGS", 0)), ST())
 torch.cuda.synchronize()
 print("ok")
