@@ -104,8 +104,9 @@ def k1_point(name, B, T, H, k, dev, hbm_peak, timeit):
     ms = timeit(lambda i: L.select_compact(P(logits), None, P(hid[i]), P(outb[i]), P(keep), P(pos), P(cu), B, Pn, H, s0, n_img, k, 0, st()), n_rot)
     nbytes = 2 * B * Pp * H * 2 + B * n_img * 4 + B * Pp * 4
     del hid, outb
+    traffic, tsrc = measured_traffic("select_compact_kernel", nbytes)
     return {"kernel": name, "bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / ms / 1e6 / hbm_peak,
-            "us": ms * 1e3, "algorithmic_bytes": nbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}
+            "us": ms * 1e3, "algorithmic_bytes": nbytes, "traffic": traffic, "traffic_source": tsrc, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}
 
 
 def rot_timeit(fn, n_rot=1, iters=20, warm=3):
@@ -499,7 +500,7 @@ def phase_and_roofline(model, eng, a, ids_d, pix_d, fd, dev):
         nbytes = int(lens_host[l].sum()) * 2 * hd * 2 * nh
         k3.append({"kernel": f"K3 dl_attn_decode_fused layer {l} ({'lo' if l < SL else 'hi'} class), kv_len {lens_host[l].tolist()}", "bound": "hbm",
                    "achieved": nbytes / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": nbytes / ms / 1e6 / peak, "us": ms * 1e3,
-                   "algorithmic_bytes": nbytes, "peak_source": how,
+                   "algorithmic_bytes": nbytes, "traffic": measured_traffic("attn_decode_kernel", nbytes)[0], "peak_source": how,
                    "note": "latency-bound at these lengths; the same layer's rows are re-read by the 20 graph-timed launches, so L2 serves them: "
                            "an upper bound on the in-step rate"})
     eng.launches = launches_before  # diagnostics only
