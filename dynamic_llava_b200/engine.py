@@ -362,9 +362,12 @@ class Engine:
     # multimodal splice  (dynamic_llava_arch.py:169-601, labels=None / attention_mask=None / one image per sample)
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def splice(self, input_ids, image_feats, max_len=None, padding_side="right"):
-        """-> (inputs_embeds [B,P,H], indices list[dict] (one per sample that has an image))."""
-        ids_host = input_ids.to("cpu")
+    def splice(self, input_ids, image_feats, max_len=None, padding_side="right", ids_host=None):
+        """-> (inputs_embeds [B,P,H], indices list[dict] (one per sample that has an image)).
+        The per-sample segment dicts are host data (the reference builds them with `.item()` reads, dynamic_llava_arch.py:330-334): when the
+        caller's ids came from the host (the usual case: tokenizer output), that copy is used and nothing is read back from the device."""
+        if ids_host is None:
+            ids_host = input_ids if input_ids.device.type == "cpu" else input_ids.to("cpu")
         B, T = ids_host.shape
         n_img = image_feats.shape[1]
         img_pos, seq_len, indices = [], [], []

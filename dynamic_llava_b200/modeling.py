@@ -227,7 +227,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
 
     # ---- prepare_inputs_labels_for_multimodal (dynamic_llava_arch.py:169-601) ----------------------------------
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images,
-                                             image_sizes=None):
+                                             image_sizes=None, ids_host=None):
         vt = self.get_vision_tower()
         if vt is None or images is None or input_ids.shape[1] == 1:  # :179-188
             return (input_ids, position_ids, attention_mask, past_key_values, None, labels), (None,)
@@ -239,7 +239,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             raise NotImplementedError("multi-image / anyres inputs are out of scope (LLaVA-1.5 'flat' single image only)")
         feats = self.encode_images(images)
         embeds, indices = self.engine.splice(input_ids, feats, max_len=getattr(self.config, "tokenizer_model_max_length", None),
-                                             padding_side=getattr(self.config, "tokenizer_padding_side", "right"))
+                                             padding_side=getattr(self.config, "tokenizer_padding_side", "right"), ids_host=ids_host)
         return (None, position_ids, attention_mask, past_key_values, embeds, None), (indices,)
 
     # ---- forward (dynamic_llava_llama.py:68-115 -> dynamic_modeling_llama.py:2631-2813) ------------------------
@@ -378,11 +378,12 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         sc = self.config.sparse_config
         eng = self.engine
         dev = self.device
+        ids_host = inputs if inputs.device.type == "cpu" else None  # host ids (tokenizer output): no device read-back for the segment dicts
         inputs = inputs.to(dev, non_blocking=True) if inputs.device != dev else inputs
         if images is not None:
             images = images.to(dev, non_blocking=True) if images.device != dev else images
             (_, _, attention_mask, _, embeds, _), (indices,) = self.prepare_inputs_labels_for_multimodal(
-                inputs, None, attention_mask, None, None, images, image_sizes=image_sizes)
+                inputs, None, attention_mask, None, None, images, image_sizes=image_sizes, ids_host=ids_host)
         else:
             embeds, indices = None, None
         if embeds is None:
