@@ -540,7 +540,8 @@ def cpu_baseline(a, steps, warmup):
     torch.set_num_threads(cores)
     cfgd = preset(a.preset)
     cfgd["sparse_config"]["vision_keep_rate"] = a.keep_rate
-    cfgd["sparse_config"]["use_output_text_predictor"] = False  # config 1: reference's image-bench setting
+    has_out = a.out_keep == "linspace(0.1,0.9)" or float(a.out_keep) >= 0
+    cfgd["sparse_config"]["use_output_text_predictor"] = has_out  # same flags as the timed workload (forced seeded decisions below)
     avail = psutil.virtual_memory().available
     need = 36e9 if "13b" in a.preset else 20e9
     if avail < need:
@@ -551,18 +552,22 @@ def cpu_baseline(a, steps, warmup):
     T_cpu = min(a.prompt_len, 32)  # config 4's 1473-id prompt (a 53 TFLOP 13B prefill) would not end within minutes on host cores
     ids, pix = synthetic_inputs(cfgd, 1, T_cpu, seed=1)
     n_new = a.cpu_new_tokens
+    from dynamic_llava_b200.synthetic import forced_text_decisions
+    rates = out_keep_rates(a) if has_out else None
+    fd_cpu = forced_text_decisions(max(n_new - 1, 1), 1, keep_rate=(rates[0] if isinstance(rates, list) else rates), seed=3) if has_out else None
     vals = []
     t_start = time.perf_counter()
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        res = O.greedy_loop(sd, cfgd, ids, pix, n_new)
+        res = O.greedy_loop(sd, cfgd, ids, pix, n_new, forced_text_decisions=fd_cpu)
         dt = time.perf_counter() - t0
         if it >= warmup:
             vals.append(n_new / dt)
         if vals and time.perf_counter() - t_start > 150.0:  # bounded: a long --steps request must still end within a few minutes
             break
     return {"value": statistics.median(vals), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{a.preset} bf16 random-init (tiled), B=1, {T_cpu}-id prompt + 1 image, keep {a.keep_rate}, {n_new} greedy tokens "
+            "sample": f"{a.preset} bf16 random-init (tiled), B=1, {T_cpu}-id prompt + 1 image, keep {a.keep_rate}, output decisions "
+                      f"{'forced, rate ' + str(rates[0] if isinstance(rates, list) else rates) if has_out else 'off'}, {n_new} greedy tokens "
                       f"(CLIP+prefill+{n_new - 1} decode steps) per step; weights built in {build_s:.0f}s (untimed)",
             "steps": len(vals)}
 

@@ -46,9 +46,62 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(const bf16* __restrict__ x
   }
 }
 
+// Many rows (prefill: B*P rows): ONE WARP per row, CH 128-bit chunks per lane all in flight at once, warp shuffles only — no block
+// barrier and 8 rows per CTA, so 1168 rows are one wave of 146 CTAs instead of two waves of 512-thread CTAs serialised on two
+// __syncthreads each (measured 9 us -> see profiles/r2_norm_warp_rows.md).
+template <int CH>
+__global__ void __launch_bounds__(256, 2) rmsnorm_rows_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                                                           int rows, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const bf16* xr = x + row * H;
+  bf16* yr = y + row * H;
+  bf16x8 cache[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) cache[i] = ld8(xr + (lane + i * 32) * 8);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    float f[8];
+    unpack8(cache[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+  }
+  ss = warp_sum(ss);
+  const float rstd = 1.0f / sqrtf(ss / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    // keep the row PACKED between the two passes (CH * 4 registers): without this the compiler carries the 8 * CH unpacked floats
+    // across the reduction and spills at CH >= 16
+    uint32_t* cw = reinterpret_cast<uint32_t*>(&cache[i]);
+    asm volatile("" : "+r"(cw[0]), "+r"(cw[1]), "+r"(cw[2]), "+r"(cw[3]));
+    float f[8], g[8];
+    unpack8(cache[i], f);
+    unpack8(ld8(w + (lane + i * 32) * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = g[j] * rbf(f[j] * rstd);
+    st8(yr + (lane + i * 32) * 8, pack8(f));
+  }
+}
+
 extern "C" int dl_rmsnorm(const void* x, const void* w, void* y, int rows, int H, float eps, cudaStream_t stream) {
   DL_REQUIRE(H % 8 == 0 && H <= 512 * 8 * 4, "dl_rmsnorm");
   if (rows == 0) return 0;
+  if (rows >= 64 && H % 256 == 0 && H / 256 <= 20) {
+    const dim3 grid((rows + 7) / 8), block(256);
+#define DL_RMS_ROWS(CH_)                                                                                                          \
+  case CH_:                                                                                                                       \
+    dl_launch_pdl(rmsnorm_rows_kernel<CH_>, grid, block, 0, stream, (const bf16*)x, (const bf16*)w, (bf16*)y, rows, H, eps); \
+    DL_CHECK_LAUNCH("dl_rmsnorm");
+    switch (H / 256) {
+      DL_RMS_ROWS(1) DL_RMS_ROWS(2) DL_RMS_ROWS(4) DL_RMS_ROWS(8) DL_RMS_ROWS(16) DL_RMS_ROWS(20)
+      default: break;
+    }
+#undef DL_RMS_ROWS
+  }
   int threads = H / 8 >= 512 ? 512 : ((H / 8 + 31) / 32) * 32;
   int per = (H / 8 + threads - 1) / threads;
   if (per <= 1)
@@ -112,10 +165,62 @@ __global__ void __launch_bounds__(512) layernorm_kernel(const bf16* __restrict__
   }
 }
 
+template <int CH>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                             const bf16* __restrict__ b, bf16* __restrict__ y, int rows, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const bf16* xr = x + row * H;
+  bf16* yr = y + row * H;
+  float f[CH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) unpack8(ld8(xr + (lane + i * 32) * 8), f[i]);
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[i][j];
+  const float mean = warp_sum(s) / (float)H;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = f[i][j] - mean;
+      v += d * d;
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    float g[8], bb[8], o[8];
+    unpack8(ld8(w + (lane + i * 32) * 8), g);
+    unpack8(ld8(b + (lane + i * 32) * 8), bb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * g[j] + bb[j];
+    st8(yr + (lane + i * 32) * 8, pack8(o));
+  }
+}
+
 extern "C" int dl_layernorm(const void* x, const void* w, const void* b, void* y, int rows, int H, float eps,
                             cudaStream_t stream) {
   DL_REQUIRE(H % 8 == 0 && H <= 512 * 8 * 4, "dl_layernorm");
   if (rows == 0) return 0;
+  if (rows >= 64 && H % 256 == 0 && H / 256 <= 8) {
+    const dim3 grid((rows + 7) / 8), block(256);
+#define DL_LN_ROWS(CH_)                                                                                                              \
+  case CH_:                                                                                                                          \
+    dl_launch_pdl(layernorm_rows_kernel<CH_>, grid, block, 0, stream, (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, H, \
+                  eps);                                                                                                              \
+    DL_CHECK_LAUNCH("dl_layernorm");
+    switch (H / 256) {
+      DL_LN_ROWS(1) DL_LN_ROWS(2) DL_LN_ROWS(4) DL_LN_ROWS(8)
+      default: break;
+    }
+#undef DL_LN_ROWS
+  }
   int threads = H / 8 >= 512 ? 512 : ((H / 8 + 31) / 32) * 32;
   int per = (H / 8 + threads - 1) / threads;
   if (per <= 1)

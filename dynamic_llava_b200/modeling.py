@@ -200,7 +200,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
                 vt._engine = ref
         return self._engine
 
-    def _session(self, B, cap_lo, cap_hi, max_new, scratch=False) -> Session:
+    def _session(self, B, cap_lo, cap_hi, max_new, scratch=False, keep_slabs=False) -> Session:
         # sparse_layer fixes the arena's lo/hi split: a caller that mutates the live sparse_config gets a new arena, not a stale split
         key = (B, cap_lo, cap_hi, max_new, scratch, self.config.sparse_config["sparse_layer"])
         s = self._sessions.get(key)
@@ -213,7 +213,10 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
             s = Session(self.engine, B, cap_lo, cap_hi, max_new)
             self._sessions[key] = s
         else:
-            s.reset(lengths_only=scratch)
+            # keep_slabs: generate() never hands the cache out, and no kernel reads a slot at or beyond kv_len, so only the lengths
+            # are cleared (re-zeroing 1.3 GB of slabs per call is 0.2 ms at 7B, B = 8); forward() returns zero-padded legacy views
+            # and therefore starts from zeroed slabs
+            s.reset(lengths_only=scratch or keep_slabs)
         return s
 
     def _past_view(self, sess) -> LegacyPastView:
@@ -400,7 +403,7 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         if sc["use_vision_predictor"] and indices is not None and len(indices) == B:
             n_img = indices[0]["image"][1] - indices[0]["image"][0]
             k_drop = n_img - int(n_img * sc["vision_keep_rate"])
-        sess = self._session(B, P + max_new, P - k_drop + max_new, max_new)
+        sess = self._session(B, P + max_new, P - k_drop + max_new, max_new, keep_slabs=True)
         a = sess.arena
         use_dec = bool(sc["use_text_predictor"] and sc["use_output_text_predictor"]) or forced_dec is not None
         if forced_dec is not None:
