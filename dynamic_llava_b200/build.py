@@ -83,5 +83,11 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def was_rebuilt(before_mtime) -> bool:
+    return (not before_mtime) or os.path.getmtime(LIB) > before_mtime
+
+
 if __name__ == "__main__":
-    print(build_extension(force="--force" in sys.argv, verbose=True))
+    t0 = os.path.getmtime(LIB) if os.path.exists(LIB) else 0
+    path = build_extension(force="--force" in sys.argv, verbose=True)
+    print(("built " if was_rebuilt(t0) else "up to date, reusing ") + path)

@@ -568,6 +568,36 @@ def test_integration_stub_sdpa_prefill(L, B, nh, Lq, Lk):
     assert (got - ref).abs().max().item() < 2e-2
 
 
+def test_integration_stub_linear_and_mlp(L):
+    """the kernel-level bindings shown in INTEGRATION.md for nn.Linear and LlamaMLP (+ residual): the reference's own tensors go in
+    unchanged ([B, L, H] activations, nn.Linear weights, gate|up concatenated once) and the results equal the reference's op sequence
+    `residual + down(act_fn(gate(x)) * up(x))` (dynamic_modeling_llama.py:299-330, :1295) evaluated in fp32 with its bf16 rounding points"""
+    B, Lq, H, I = 2, 150, 512, 1024
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, Lq, H, generator=g).to(BF).to(DEV)
+    res = torch.randn(B, Lq, H, generator=g).to(BF).to(DEV)
+    wg, wu, wd = [(torch.randn(*s_, generator=g) * 0.05).to(BF).to(DEV) for s_ in ((I, H), (I, H), (H, I))]
+    bias = (torch.randn(H, generator=g) * 0.1).to(BF).to(DEV)
+    ws = _linear_ws(L)
+    # linear(x, weight, bias, act=1): Linear + GELU as in the predictors / projector
+    x2 = x.reshape(-1, H)
+    y = torch.empty(B * Lq, H, device=DEV, dtype=BF)
+    wsq = (torch.randn(H, H, generator=g) * 0.05).to(BF).to(DEV)
+    L.linear(P(x2), P(wsq), P(bias), None, P(y), B * Lq, H, H, 1, P(ws), ST())
+    want = F.gelu((x2.float() @ wsq.float().T + bias.float()).to(BF).float()).to(BF)
+    # mlp(x, w_gate_up, w_down, residual)
+    wgu = torch.cat([wg, wu], 0).contiguous()
+    act = torch.empty(B * Lq, I, device=DEV, dtype=BF)
+    L.linear_swiglu(P(x2), P(wgu), P(act), B * Lq, I, H, P(ws), ST())
+    out = res.clone().reshape(-1, H)
+    L.linear(P(act), P(wd), None, P(out), P(out), B * Lq, H, I, 0, P(ws), ST())
+    torch.cuda.synchronize()
+    assert (y.float() - want.float()).abs().max() < 2e-2 * max(1.0, want.float().abs().max().item())
+    a_ref = (F.silu((x2.float() @ wg.float().T).to(BF).float()).to(BF).float() * (x2.float() @ wu.float().T).to(BF).float()).to(BF)
+    o_ref = (res.reshape(-1, H).float() + (a_ref.float() @ wd.float().T).to(BF).float()).to(BF)
+    assert (out.float() - o_ref.float()).abs().max() < 2e-2 * max(1.0, o_ref.float().abs().max().item())
+
+
 def test_attn_prefill_full_size_config4_against_sdpa(L):
     """BASELINE config 4 per GPU at full size (13B: 40 heads, B=4, L=2048 and the post-compaction L=1587): the persistent kernel against
     torch's fp32 causal SDPA of the same bf16 operands on the device, and the size-independent row property softmax-weights-sum-to-one
