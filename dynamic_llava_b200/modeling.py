@@ -151,7 +151,12 @@ class DynamicLlavaLlamaForCausalLM(nn.Module):
         return self.lm_head
 
     def resize_token_embeddings(self, n: int):
-        """dynamic_llava_builder.py:235: grow/shrink embed_tokens and lm_head rows (new rows zero)."""
+        """dynamic_llava_builder.py:235: grow/shrink embed_tokens and lm_head rows (new rows zero).
+        The weight-streaming and tile GEMMs address rows in 16-byte units: a vocabulary that is not a multiple of 8 is refused by name
+        (LLaVA-1.5 checkpoints keep the 32000-entry Vicuna vocabulary: `mm_use_im_patch_token` / `mm_use_im_start_end` are false)."""
+        if n % 8 != 0:
+            raise NotImplementedError(f"vocab size {n} is not a multiple of 8 (TMA row stride): pad the tokenizer, e.g. "
+                                      f"tokenizer.add_tokens([...]) up to {-(-n // 8) * 8} entries, before resize_token_embeddings")
         for holder in (self.model.embed_tokens, self.lm_head):
             old = holder.weight.data
             new = torch.zeros(n, old.shape[1], device=old.device, dtype=old.dtype)
