@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "prefill+decode tokens/sec @ LLaVA-1.5-7B, vision_keep_rate=0.2"
 UNIT = "tokens/s"
+DT = torch.bfloat16  # element type of the B200 arm (--dtype)
 
 
 def parse():
@@ -36,6 +37,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="element type of the B200 arm: bf16 (libdynllava_b200.so, the measured default) or fp16 (libdynllava_b200_f16.so)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config (1-based): 2 = the config the metric is quoted on (default); 3 = ragged-KV stress (B=8 per GPU, "
                          "256 tokens, per-sample forced keep rates linspace(0.1,0.9,8); meant for --gpus 8 = batch 64); 4 = 13B, B=4 per GPU "
@@ -88,16 +91,16 @@ def k1_point(name, B, T, H, k, dev, hbm_peak, timeit):
     """K1 (select + gather/compact) on one shape, graph-timed, buffers rotated beyond the 126 MB L2; bytes = SURVEY.md §8d's formula"""
     import ctypes
     from dynamic_llava_b200._lib import lib
-    L = lib()
+    L = lib(DT)
     P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     n_img, s0 = 576, 5
     Pn = T - 1 + n_img
     Pp = Pn - n_img + k
     n_rot = max(2, int(300e6 // (B * Pn * H * 2)) + 1)
-    hid = [torch.randn(B, Pn, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
-    outb = [torch.empty(B, Pp, H, device=dev, dtype=torch.bfloat16) for _ in range(n_rot)]
-    logits = torch.randn(B, n_img, 2, device=dev, dtype=torch.bfloat16)
+    hid = [torch.randn(B, Pn, H, device=dev, dtype=DT) for _ in range(n_rot)]
+    outb = [torch.empty(B, Pp, H, device=dev, dtype=DT) for _ in range(n_rot)]
+    logits = torch.randn(B, n_img, 2, device=dev, dtype=DT)
     keep = torch.empty(B, k, dtype=torch.int64, device=dev)
     pos = torch.empty(B, Pp, dtype=torch.int32, device=dev)
     cu = torch.empty(B + 1, dtype=torch.int32, device=dev)
@@ -179,7 +182,7 @@ def kernel_rooflines(dev):
     import ctypes
     import math
     from dynamic_llava_b200._lib import lib
-    L = lib()
+    L = lib(DT)
     P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -192,10 +195,10 @@ def kernel_rooflines(dev):
     for name, B, nh, Lq in (("K2 dl_attn_prefill_tc4 L=2048 B=8 32 heads (stress)", 8, 32, 2048), ("K2 dl_attn_prefill_tc4 L=607 B=8 (layers 0-1)", 8, 32, 607),
                             ("K2 dl_attn_prefill_tc4 L=146 B=8 (layers 2-31)", 8, 32, 146)):
         hd, H, cap, N = 128, nh * 128, Lq + 8, B * Lq
-        qkv = torch.randn(N, 3 * H, device=dev, dtype=torch.bfloat16)
-        K = torch.randn(B, nh, cap, hd, device=dev, dtype=torch.bfloat16)
-        V = torch.randn(B, nh, cap, hd, device=dev, dtype=torch.bfloat16)
-        o = torch.empty(N, H, device=dev, dtype=torch.bfloat16)
+        qkv = torch.randn(N, 3 * H, device=dev, dtype=DT)
+        K = torch.randn(B, nh, cap, hd, device=dev, dtype=DT)
+        V = torch.randn(B, nh, cap, hd, device=dev, dtype=DT)
+        o = torch.empty(N, H, device=dev, dtype=DT)
         cu = torch.arange(0, (B + 1) * Lq, Lq, device=dev, dtype=torch.int32)
         past = torch.zeros(B, device=dev, dtype=torch.int32)
         ms = timeit(lambda i: L.attn_prefill_tc4(P(qkv), 3 * H, P(K), P(V), P(o), H, P(cu), P(past), N, B, nh, cap, Lq, 1.0 / math.sqrt(hd), 0, st()),
@@ -290,9 +293,9 @@ def run_b200(a):
     cfgd["sparse_config"]["vision_keep_rate"] = a.keep_rate
     cfgd["sparse_config"]["use_output_text_predictor"] = has_out
     cfg = DynamicLlavaConfig(**cfgd)
-    model = DynamicLlavaLlamaForCausalLM(cfg, device=dev)
+    model = DynamicLlavaLlamaForCausalLM(cfg, device=dev, dtype=DT)
     model.get_vision_tower().load_model()
-    sd = device_state_dict(cfgd, seed=0, device=dev)  # same weights on every replica
+    sd = device_state_dict(cfgd, seed=0, device=dev, dtype=DT)  # same weights on every replica
     model.load_state_dict(sd, strict=True)
     del sd
     torch.cuda.empty_cache()
@@ -300,7 +303,7 @@ def run_b200(a):
     eng._check_packed()
 
     B, T, NN = a.batch, a.prompt_len, a.new_tokens
-    ids_h, pix_h = synthetic_inputs(cfgd, B, T, seed=1 + rank)  # each rank owns its own chunk of the global batch
+    ids_h, pix_h = synthetic_inputs(cfgd, B, T, seed=1 + rank, dtype=DT)  # each rank owns its own chunk of the global batch
     fd = forced_text_decisions(max(NN - 1, 1), B, keep_rate=out_keep_rates(a), seed=3 + rank) if has_out else None
     ids_pin, pix_pin = ids_h.pin_memory(), pix_h.pin_memory()
     ids_d, pix_d = ids_h.to(dev), pix_h.to(dev)
@@ -356,7 +359,7 @@ def run_b200(a):
     total_tokens = world * B * NN * a.steps
     line = {
         "metric": METRIC, "value": total_tokens / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
         "data": "synthetic (seeded randn 336x336 pixels, random ids, N(0,0.02) random-init weights)",
         "config": {"workload": workload_name(a, world),
                    "baseline_config": a.config, "global_batch": world * B, "prompt_ids": T, "new_tokens": NN,
@@ -629,6 +632,7 @@ def run_reference(a):
 
 if __name__ == "__main__":
     args = parse()
+    DT = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     if args.impl == "reference":
         run_reference(args)
     else:

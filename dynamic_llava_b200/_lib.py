@@ -1,4 +1,4 @@
-"""ctypes binding of libdynllava_b200.so.  Signatures are parsed from include/dynllava_b200.h, so the header is the
+"""ctypes binding of libdynllava_b200.so (bfloat16) and libdynllava_b200_f16.so (float16).  Signatures are parsed from include/dynllava_b200.h, so the header is the
 single source of truth for the C ABI.  There is NO fallback: if the library is missing or a call fails, this raises."""
 from __future__ import annotations
 
@@ -10,6 +10,7 @@ from typing import Dict, List, Tuple
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "dynllava_b200.h")
 LIB_PATH = os.path.join(HERE, "csrc", "libdynllava_b200.so")
+LIB_PATH_F16 = os.path.join(HERE, "csrc", "libdynllava_b200_f16.so")
 
 _CTYPES = {
     "int": ctypes.c_int,
@@ -69,7 +70,7 @@ class DynLlavaLib:
 
         def call(*args):
             rc = raw(*args)
-            if raw.restype is ctypes.c_int and rc != 0 and name not in ("version", "device_is_sm100", "skinny_gemm_splits"):
+            if raw.restype is ctypes.c_int and rc != 0 and name not in ("version", "element_type", "device_is_sm100", "skinny_gemm_splits"):
                 raise RuntimeError(f"dl_{name} failed ({rc}): {self._dl_last_error_string().decode()}")
             return rc
 
@@ -77,11 +78,17 @@ class DynLlavaLib:
         return call
 
 
-_LIB = None
+_LIBS: Dict[str, DynLlavaLib] = {}
 
 
-def lib() -> DynLlavaLib:
-    global _LIB
-    if _LIB is None:
-        _LIB = DynLlavaLib()
-    return _LIB
+def lib(dtype=None) -> DynLlavaLib:
+    """The library whose element type is `dtype` (torch.bfloat16 — the default — or torch.float16; strings accepted)."""
+    key = "f16" if str(dtype) in ("torch.float16", "float16", "fp16", "f16") else "bf16"
+    if dtype is not None and key == "bf16" and str(dtype) not in ("torch.bfloat16", "bfloat16", "bf16"):
+        raise RuntimeError(f"no kernel library computes in {dtype}: load the model in torch.bfloat16 or torch.float16")
+    if key not in _LIBS:
+        L = DynLlavaLib(LIB_PATH_F16 if key == "f16" else LIB_PATH)
+        if L.element_type() != (1 if key == "f16" else 0):
+            raise RuntimeError(f"{L._dll._name}: element type {L.element_type()} does not match the requested {key} build")
+        _LIBS[key] = L
+    return _LIBS[key]

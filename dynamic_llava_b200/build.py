@@ -1,4 +1,5 @@
-"""Build libdynllava_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+"""Build libdynllava_b200.so (bfloat16) and libdynllava_b200_f16.so (float16, -DDL_HALF) in-tree with nvcc for sm_100a
+(cross-compiles without a GPU).  Both come from the same sources and export the same symbols.
 
     python -m dynamic_llava_b200.build [--force]
 
@@ -16,6 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdynllava_b200.so")
+LIB_F16 = os.path.join(CSRC, "libdynllava_b200_f16.so")
 SOURCES = [
     "abi.cu",
     "elementwise.cu",
@@ -54,18 +56,25 @@ def _stale(out: str, deps) -> bool:
 
 
 def build_extension(force: bool = False, verbose: bool = False) -> str:
+    """-> path of the bf16 library; the fp16 one is built next to it."""
+    _build_one(LIB, "build", [], force, verbose)
+    _build_one(LIB_F16, "build_f16", ["-DDL_HALF"], force, verbose)
+    return LIB
+
+
+def _build_one(LIB: str, objdir_name: str, defines, force: bool, verbose: bool) -> str:
     hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "dynllava_b200.h")]
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and not _stale(LIB, srcs + hdrs):
         return LIB  # up to date (the GPU box receives the prebuilt .so with the snapshot)
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + list(defines) + ["-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -84,10 +93,10 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
 
 
 def was_rebuilt(before_mtime) -> bool:
-    return (not before_mtime) or os.path.getmtime(LIB) > before_mtime
+    return (not before_mtime) or max(os.path.getmtime(LIB), os.path.getmtime(LIB_F16)) > before_mtime
 
 
 if __name__ == "__main__":
-    t0 = os.path.getmtime(LIB) if os.path.exists(LIB) else 0
+    t0 = min(os.path.getmtime(LIB), os.path.getmtime(LIB_F16)) if os.path.exists(LIB) and os.path.exists(LIB_F16) else 0
     path = build_extension(force="--force" in sys.argv, verbose=True)
-    print(("built " if was_rebuilt(t0) else "up to date, reusing ") + path)
+    print(("built " if was_rebuilt(t0) else "up to date, reusing ") + path + " and " + LIB_F16)

@@ -60,14 +60,12 @@ def load_model_from_dir(model_path, device="cuda", torch_dtype=None):
     """`DynamicLlavaLlamaForCausalLM.from_pretrained` for an HF-format checkpoint directory (dynamic_llava_builder.py:191-193 +
     :237-242): `config.json` with `sparse_config` + `*.safetensors` / `pytorch_model*.bin` shards under the reference's keys; the CLIP
     tower comes from the checkpoint itself or from a local `mm_vision_tower` directory (no hub access).
-    The kernels compute in bf16: a float16 request (the reference's eval default, dynamic_llava_builder.py:62) is served in bf16 with a
-    warning, any other dtype is refused."""
-    if torch_dtype not in (None, torch.bfloat16, "bfloat16", "auto"):
-        if torch_dtype in (torch.float16, "float16"):
-            warnings.warn("torch_dtype=float16 requested: the B200 kernels compute in bfloat16; weights are cast to bf16 "
-                          "(same 16-bit storage, wider exponent, 3 fewer mantissa bits than the reference's fp16 eval runs)")
-        else:
-            raise NotImplementedError(f"torch_dtype={torch_dtype}: the B200 path runs in bfloat16 only")
+    `torch_dtype`: torch.bfloat16 (default) or torch.float16 (what the reference's eval drivers load,
+    dynamic_llava_builder.py:62) — each has its own kernel library; any other dtype is refused."""
+    dt = {None: torch.bfloat16, "auto": torch.bfloat16, "bfloat16": torch.bfloat16, torch.bfloat16: torch.bfloat16,
+          "float16": torch.float16, torch.float16: torch.float16}.get(torch_dtype)
+    if dt is None:
+        raise NotImplementedError(f"torch_dtype={torch_dtype}: the B200 path runs in bfloat16 or float16 only")
     cfg_json = json.load(open(os.path.join(model_path, "config.json")))
     if "sparse_config" not in cfg_json:
         raise KeyError("config.json has no `sparse_config`: not a Dynamic-LLaVA checkpoint (train_sparse.py:1007-1008)")
@@ -89,7 +87,7 @@ def load_model_from_dir(model_path, device="cuda", torch_dtype=None):
                              vision=_vision_config(cfg_json))
     if cfg.num_key_value_heads != cfg.num_attention_heads:
         raise NotImplementedError("grouped-query attention is not used by LLaVA-1.5 and not supported")
-    model = DynamicLlavaLlamaForCausalLM(cfg, device=device, dtype=torch.bfloat16)
+    model = DynamicLlavaLlamaForCausalLM(cfg, device=device, dtype=dt)
     model.get_vision_tower().load_model()
     sd = _load_shards(model_path)
     if not any(k.startswith(_CLIP_PREFIX) for k in sd):  # tower weights live in their own directory (clip_encoder.py:36-38)
@@ -111,7 +109,9 @@ def load_model_from_dir(model_path, device="cuda", torch_dtype=None):
 
 
 def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, load_4bit=False, device_map="auto", device="cuda",
-                          use_flash_attn=False, **kwargs):
+                          use_flash_attn=False, torch_dtype=torch.float16, **kwargs):
+    """dynamic_llava_builder.py:26-243.  Like the reference (:62) the model is loaded in float16 unless told otherwise;
+    pass torch_dtype=torch.bfloat16 for the bf16 kernels (the configuration bench.py measures)."""
     if load_8bit or load_4bit:
         raise NotImplementedError("bitsandbytes 8-/4-bit loading is out of scope (quantised variants)")
     if model_base is not None or "lora" in model_name.lower():
@@ -119,7 +119,7 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
     if "llava" not in model_name.lower():
         raise NotImplementedError("only Dynamic-LLaVA (Llama) checkpoints are supported; MPT/Mistral are other model families")
     dev = device if device != "cuda" or device_map in ("auto", None) else device_map
-    model = load_model_from_dir(model_path, device=dev)
+    model = load_model_from_dir(model_path, device=dev, torch_dtype=torch_dtype)
     cfg = model.config
 
     tokenizer = None

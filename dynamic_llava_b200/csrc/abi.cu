@@ -16,6 +16,11 @@ extern "C" int dl_set_error(int code, const char* where) {
 }
 extern "C" const char* dl_last_error_string(void) { return g_err; }
 extern "C" int dl_version(void) { return DL_B200_ABI_VERSION; }
+#ifdef DL_HALF
+extern "C" int dl_element_type(void) { return 1; }
+#else
+extern "C" int dl_element_type(void) { return 0; }
+#endif
 extern "C" int dl_device_is_sm100(void) {
   int dev = 0;
   cudaDeviceProp prop;

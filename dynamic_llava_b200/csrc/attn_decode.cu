@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
             if (kk < nk) {
               const float p = (u == sub) ? pm[i] : po[i];
               const uint2 raw = *reinterpret_cast<const uint2*>(Vs + (wk0 + kk) * AD_HD + lane * 4);
-              const float2 v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-              const float2 v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+              const float2 v01 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.x));
+              const float2 v23 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.y));
               acc[0] += p * v01.x;
               acc[1] += p * v01.y;
               acc[2] += p * v23.x;
@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(
         v23 = make_float2(S.vn[lane * 4 + 2], S.vn[lane * 4 + 3]);
       } else {
         const uint2 raw = *reinterpret_cast<const uint2*>(v_side + ((int64_t)b * heads + h) * AD_HD + lane * 4);
-        v01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-        v23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        v01 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.x));
+        v23 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.y));
       }
       acc[0] = acc[0] * alpha + p * v01.x;
       acc[1] = acc[1] * alpha + p * v01.y;

@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) attn_prefill_tc4_kernel(
             const float p1 = (EXP_POLY && (e & 6) == 4) ? t4_ex2_poly(x1) : t4_ex2(x1);  // ... and 5 of every 8: 1 in 4
             ls0 += p0;
             ls1 += p1;
-            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+            bf16x2 t = f2bf2(p0, p1);
             pk[(e >> 1) & 15] = *reinterpret_cast<uint32_t*>(&t);
           }
           tmem_st_32x32b_x16(tsj + hh * 16, pk);  // P overwrites S columns this thread has already read; the first store

@@ -2,10 +2,25 @@
 // PTX spellings follow the CUDA 12.9 PTX ISA (tcgen05 / cp.async.bulk / mbarrier).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Element type of this build.  The same sources are compiled twice: libdynllava_b200.so computes in bfloat16 (default)
+// and libdynllava_b200_f16.so (-DDL_HALF) in float16, the dtype the reference's eval drivers load
+// (llava/model/dynamic_llava_builder.py:62).  Every kernel spells the element type `bf16` and converts only through
+// the helpers below, so the two builds differ in these typedefs, the UMMA operand format and the tensor-map data type.
+#ifdef DL_HALF
+typedef __half bf16;
+typedef __half2 bf16x2;
+#define DL_UMMA_AB_FORMAT 0u  // F16
+#define DL_DTYPE_CODE 1
+#else
 typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf16x2;
+#define DL_UMMA_AB_FORMAT 1u  // BF16
+#define DL_DTYPE_CODE 0
+#endif
 
 #define DL_DEVINL __device__ __forceinline__
 
@@ -54,18 +69,27 @@ static inline cudaError_t dl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
 // bf16 <-> fp32, 128-bit vectors
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  bf16x2 v[4];
 };
 
+#ifdef DL_HALF
+DL_DEVINL float bf2f(bf16 x) { return __half2float(x); }
+DL_DEVINL bf16 f2bf(float x) { return __float2half_rn(x); }
+DL_DEVINL float2 bf2f2(bf16x2 v) { return __half22float2(v); }
+DL_DEVINL bf16x2 f2bf2(float a, float b) { return __floats2half2_rn(a, b); }
+#else
 DL_DEVINL float bf2f(bf16 x) { return __bfloat162float(x); }
 DL_DEVINL bf16 f2bf(float x) { return __float2bfloat16_rn(x); }
-// round-trip through bf16: the "bf16 tensor op" rounding point of the reference's eager PyTorch graph
-DL_DEVINL float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+DL_DEVINL float2 bf2f2(bf16x2 v) { return __bfloat1622float2(v); }
+DL_DEVINL bf16x2 f2bf2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+#endif
+// round-trip through the element type: the "16-bit tensor op" rounding point of the reference's eager PyTorch graph
+DL_DEVINL float rbf(float x) { return bf2f(f2bf(x)); }
 
 DL_DEVINL void unpack8(const bf16x8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
+    float2 t = bf2f2(p.v[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -73,7 +97,7 @@ DL_DEVINL void unpack8(const bf16x8& p, float* f) {
 DL_DEVINL bf16x8 pack8(const float* f) {
   bf16x8 p;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) p.v[i] = f2bf2(f[2 * i], f[2 * i + 1]);
   return p;
 }
 DL_DEVINL bf16x8 ld8(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
@@ -244,8 +268,8 @@ DL_DEVINL uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, A and B K-major.
 DL_DEVINL constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4)                       // c_format = F32
-         | (1u << 7)                     // a_format = BF16
-         | (1u << 10)                    // b_format = BF16
+         | (DL_UMMA_AB_FORMAT << 7)      // a_format = BF16 (F16 in the -DDL_HALF build)
+         | (DL_UMMA_AB_FORMAT << 10)     // b_format
          | ((uint32_t)a_mn_major << 15)  // a_major
          | ((uint32_t)b_mn_major << 16)  // b_major
          | ((uint32_t)(N >> 3) << 17)    // n_dim

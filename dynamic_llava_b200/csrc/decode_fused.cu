@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) dec_reduce_bf16_kernel(const float* __res
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= MN) return;
   const float4 a = sum_slices4(partial + i, MN, S);
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+  bf16x2 lo = f2bf2(a.x, a.y), hi = f2bf2(a.z, a.w);
   uint2 o;
   o.x = *reinterpret_cast<uint32_t*>(&lo);
   o.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -67,13 +67,13 @@ __global__ void __launch_bounds__(RN_THREADS) dec_reduce_residual_norm_kernel(co
     if (i < H) {
       const uint2 raw = *reinterpret_cast<const uint2*>(x + (int64_t)m * H + i);
       const float4 a = sum_slices_f4(partial + (int64_t)m * H + i, slice, S);
-      const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      const float2 x01 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.x));
+      const float2 x23 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.y));
       r[v][0] = rbf(x01.x + rbf(a.x));
       r[v][1] = rbf(x01.y + rbf(a.y));
       r[v][2] = rbf(x23.x + rbf(a.z));
       r[v][3] = rbf(x23.y + rbf(a.w));
-      __nv_bfloat162 lo = __floats2bfloat162_rn(r[v][0], r[v][1]), hi = __floats2bfloat162_rn(r[v][2], r[v][3]);
+      bf16x2 lo = f2bf2(r[v][0], r[v][1]), hi = f2bf2(r[v][2], r[v][3]);
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&lo);
       o.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -90,10 +90,10 @@ __global__ void __launch_bounds__(RN_THREADS) dec_reduce_residual_norm_kernel(co
     const int i = (threadIdx.x + v * RN_THREADS) * 4;
     if (i < H) {
       const uint2 raw = wraw[v];
-      const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-      __nv_bfloat162 lo = __floats2bfloat162_rn(w01.x * rbf(r[v][0] * rstd), w01.y * rbf(r[v][1] * rstd));
-      __nv_bfloat162 hi = __floats2bfloat162_rn(w23.x * rbf(r[v][2] * rstd), w23.y * rbf(r[v][3] * rstd));
+      const float2 w01 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.x));
+      const float2 w23 = bf2f2(*reinterpret_cast<const bf16x2*>(&raw.y));
+      bf16x2 lo = f2bf2(w01.x * rbf(r[v][0] * rstd), w01.y * rbf(r[v][1] * rstd));
+      bf16x2 hi = f2bf2(w23.x * rbf(r[v][2] * rstd), w23.y * rbf(r[v][3] * rstd));
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&lo);
       o.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) dec_reduce_swiglu_kernel(const float* __r
   float o[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) o[e] = rbf(gg[e] / (1.0f + expf(-gg[e]))) * uu[e];
-  __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+  bf16x2 lo = f2bf2(o[0], o[1]), hi = f2bf2(o[2], o[3]);
   uint2 w;
   w.x = *reinterpret_cast<uint32_t*>(&lo);
   w.y = *reinterpret_cast<uint32_t*>(&hi);

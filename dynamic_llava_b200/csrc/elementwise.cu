@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const bf16* __restrict__ pi
   const int py = patch / G, px = patch % G;
   bf16* dst = out + ((int64_t)b * G * G + patch) * Kpad;
   for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
-    bf16 v = __float2bfloat16(0.f);
+    bf16 v = f2bf(0.f);
     if (k < K) {
       int c = k / (ps * ps), rem = k % (ps * ps), ky = rem / ps, kx = rem % ps;
       v = pix[(((int64_t)b * C + c) * S + (py * ps + ky)) * S + (px * ps + kx)];

@@ -19,7 +19,7 @@ __global__ void turn_decision_kernel(const bf16* __restrict__ logits, const uint
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= B * Tq) return;
   bool d = forced != nullptr ? forced[n] != 0
-                             : __bfloat162float(logits[2 * n]) > __bfloat162float(logits[2 * n + 1]);
+                             : bf2f(logits[2 * n]) > bf2f(logits[2 * n + 1]);
   if (force_last && (n % Tq) == Tq - 1) d = true;
   keep[n] = d ? 1 : 0;
 }
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) kv_compact_turn_kernel(bf16* __restrict__
   __syncthreads();
   bf16x8 z;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) z.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+  for (int i = 0; i < 4; ++i) z.v[i] = f2bf2(0.f, 0.f);
   for (int it = n_kept * VCH + threadIdx.x; it < Tq * VCH; it += 256) st8(base + (int64_t)it * 8, z);
 }
 

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) output_rank_kernel(const bf16* __restrict
   const bf16* lg = logits + (int64_t)b * n * 2;
   int c = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float l0 = __bfloat162float(lg[2 * i]), l1 = __bfloat162float(lg[2 * i + 1]);
+    const float l0 = bf2f(lg[2 * i]), l1 = bf2f(lg[2 * i + 1]);
     s_score[i] = l0;
     c += l0 > l1 ? 1 : 0;
   }

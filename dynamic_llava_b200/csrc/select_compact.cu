@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(SC_BLOCK) select_compact_kernel(
   } else if (k > 0) {
     // scores rounded where the reference's bf16 log_softmax rounds, mapped to order-preserving 16-bit keys
     for (int i = tid; i < n_img; i += SC_THREADS) {
-      const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(logits + ((int64_t)b * n_img + i) * 2);
+      const bf16x2 l = *reinterpret_cast<const bf16x2*>(logits + ((int64_t)b * n_img + i) * 2);
       const float l0 = __low2float(l), l1 = __high2float(l);
       const float m = fmaxf(l0, l1);
       const bf16 sc = f2bf((l0 - m) - logf(expf(l0 - m) + expf(l1 - m)));

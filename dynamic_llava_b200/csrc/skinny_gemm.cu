@@ -14,6 +14,11 @@
 #include <string.h>
 
 #include "common.cuh"
+#ifdef DL_HALF
+#define DL_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#else
+#define DL_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#endif
 #include "../../include/dynllava_b200.h"
 
 #define SG_BM 128
@@ -241,7 +246,7 @@ extern "C" int dl_make_tmap_2d(void* out_map, const void* base, uint64_t rows, u
   cuuint64_t strides[1] = {row_stride_elems * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc((CUtensorMap*)out_map, DL_TMAP_DTYPE, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return dl_set_error((int)r, "cuTensorMapEncodeTiled");

@@ -81,15 +81,15 @@ class Engine:
     def __init__(self, model):
         if not torch.cuda.is_available():
             raise RuntimeError("dynamic_llava_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.L = lib()
-        if not self.L.device_is_sm100():
-            raise RuntimeError("dynamic_llava_b200 kernels are built for sm_100a (B200) only")
         self._model = weakref.ref(model)
         self.cfg = model.config
         self.device = model.lm_head.weight.device
         self.dtype = model.lm_head.weight.dtype
-        if self.dtype != torch.bfloat16:
-            raise RuntimeError("kernels compute in bf16: load the model with torch_dtype=torch.bfloat16")
+        if self.dtype not in (torch.bfloat16, torch.float16):
+            raise RuntimeError("kernels compute in bf16 or fp16: load the model with torch_dtype=torch.bfloat16 / torch.float16")
+        self.L = lib(self.dtype)  # libdynllava_b200.so (bf16) or libdynllava_b200_f16.so (fp16): same symbols
+        if not self.L.device_is_sm100():
+            raise RuntimeError("dynamic_llava_b200 kernels are built for sm_100a (B200) only")
         self.packed = None
         self.side_stream = torch.cuda.Stream(device=self.device)  # text-predictor branch of the decode step
         self._cu_cache = {}

@@ -6,6 +6,11 @@
  * code it replaces (paths relative to llava/model/; DML = language_model/dynamic_modeling_llama.py,
  * CU = language_model/cache_utils.py, ARCH = dynamic_llava_arch.py, CTL = language_model/custom_transformer_layer.py).
  *
+ * Two libraries are built from the same sources and export the same symbols: libdynllava_b200.so computes in
+ * bfloat16, libdynllava_b200_f16.so in float16 (the dtype the reference's eval drivers load,
+ * dynamic_llava_builder.py:62); dl_element_type() says which one is loaded.  "bf16" below means "the library's
+ * 16-bit element type".
+ *
  * Conventions: every pointer is a DEVICE pointer owned by the caller (kernels never allocate or free); tensors are
  * bf16 unless stated; all calls are asynchronous on `stream`; return 0 on success, a cudaError_t value (>0) or a
  * negative argument error otherwise; dl_last_error_string() describes the last failure on the calling thread.
@@ -21,10 +26,11 @@
 extern "C" {
 #endif
 
-#define DL_B200_ABI_VERSION 6  /* 6: superseded attention kernels (warp-MMA dl_attn_varlen, non-persistent dl_attn_prefill_tc2 / dl_attn_packed_tc) removed; 5: dl_linear / dl_linear_swiglu (2-CTA tcgen05 GEMM) replace dl_gemm_bias_act; 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points;
+#define DL_B200_ABI_VERSION 7  /* 7: dl_element_type (bf16 and fp16 builds); 6: superseded attention kernels (warp-MMA dl_attn_varlen, non-persistent dl_attn_prefill_tc2 / dl_attn_packed_tc) removed; 5: dl_linear / dl_linear_swiglu (2-CTA tcgen05 GEMM) replace dl_gemm_bias_act; 2: persistent attention (tc4) added, v1 tcgen05 attention removed; 3: instruct-predictor entry points;
                                  * 4: no-KV-cache output sparsification (dl_output_rank / dl_output_keep_index) */
 
 int dl_version(void);
+int dl_element_type(void); /* 0: bfloat16 (libdynllava_b200.so), 1: float16 (libdynllava_b200_f16.so) */
 const char* dl_last_error_string(void);
 int dl_device_is_sm100(void);
 int dl_set_error(int code, const char* where); /* internal */

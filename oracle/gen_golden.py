@@ -147,12 +147,19 @@ def run_reference(model, input_ids, pixels, n_new, forced_dec=None, forced_keep=
     return res
 
 
-def main():
+FP16_CASES = [
+    # the reference's eval drivers load torch_dtype=float16 (llava/dynamic_eval/model_vqa_loader.py:82 via builder.py:26)
+    ("toy_fp16_b1_natural", torch.float16, 1, 12, 8, False, True),
+    ("toy_fp16_b2_forced", torch.float16, 2, 12, 12, True, True),
+]
+
+
+def main(cases=None):
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(8)
     cfg = preset("toy")
-    cases = [
+    cases = cases or [
         # name, dtype, B, T, n_new, forced decisions?, output predictor on?
         ("toy_fp32_b1_natural", torch.float32, 1, 12, 8, False, True),
         ("toy_fp32_b2_natural", torch.float32, 2, 12, 8, False, True),
@@ -174,7 +181,7 @@ def main():
             res.update(name=name, dtype=str(dtype), B=B, T=T, n_new=n_new, weight_seed=0, input_seed=1,
                        forced_decisions=fd, use_output_text_predictor=out_pred, preset="toy",
                        torch_version=torch.__version__)
-            if name != "toy_bf16_b2_forced":  # keep the repo small: KV dumps only where a test reads them
+            if name not in ("toy_bf16_b2_forced", "toy_fp16_b2_forced"):  # keep the repo small: KV dumps only where a test reads them
                 res.pop("k_last"), res.pop("v_last")
             torch.save(res, os.path.join(out_dir, name + ".pt"))
             print(name, "tokens", res["tokens"].tolist(), "kv", res["kv_shapes"].tolist(),
@@ -489,6 +496,8 @@ if __name__ == "__main__":
     only = [a for a in sys.argv[1:] if a.startswith("--only-")]
     if not only:
         main()
+    if not only or "--only-fp16" in only:
+        main(FP16_CASES)
     with tempfile.TemporaryDirectory(dir=os.path.join(ROOT, "oracle")) as scratch:
         if not only:
             multiround_case(os.path.join(ROOT, "tests", "golden"), scratch)

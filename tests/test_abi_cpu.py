@@ -13,16 +13,20 @@ from dynamic_llava_b200 import _lib, build
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def so_path():
-    return build.build_extension()
+@pytest.fixture(scope="module", params=["bf16", "f16"])
+def so_path(request):
+    """both builds of the same sources: libdynllava_b200.so (bfloat16) and libdynllava_b200_f16.so (float16)"""
+    build.build_extension()
+    return build.LIB if request.param == "bf16" else build.LIB_F16
 
 
 def test_library_builds_and_loads(so_path):
     assert os.path.exists(so_path)
     dll = ctypes.CDLL(so_path)
     dll.dl_version.restype = ctypes.c_int
-    assert dll.dl_version() == 6
+    assert dll.dl_version() == 7
+    dll.dl_element_type.restype = ctypes.c_int
+    assert dll.dl_element_type() == (1 if so_path.endswith("_f16.so") else 0)
     dll.dl_last_error_string.restype = ctypes.c_char_p
     assert isinstance(dll.dl_last_error_string(), bytes)
 

@@ -81,7 +81,7 @@ def _tie_aware_keep_agreement(vision_logits_ref, keep_ref, keep_got):
     return same / float(B * k), near
 
 
-def _run_config(tag, preset_name, B, T, n_new, keep_rate, fd, quirk, per_sample_rows=None, seed=0):
+def _run_config(tag, preset_name, B, T, n_new, keep_rate, fd, quirk, per_sample_rows=None, seed=0, dtype=BF):
     """one BASELINE config (per GPU) against the device-resident oracle; returns the report row"""
     from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
     t_start = time.perf_counter()
@@ -89,12 +89,12 @@ def _run_config(tag, preset_name, B, T, n_new, keep_rate, fd, quirk, per_sample_
     cfgd["sparse_config"]["vision_keep_rate"] = keep_rate
     cfgd["sparse_config"]["use_output_text_predictor"] = fd is not None
     dev = torch.device("cuda")
-    sd16 = device_state_dict(cfgd, seed=seed, device=dev)  # independent draws per tensor
-    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device=dev)
+    sd16 = device_state_dict(cfgd, seed=seed, device=dev, dtype=dtype)  # independent draws per tensor
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device=dev, dtype=dtype)
     model.get_vision_tower().load_model()
     model.load_state_dict(sd16, strict=True)
     model.config.reference_batched_quirk = quirk
-    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1, dtype=dtype)
     ids, pix = ids.to(dev), pix.to(dev)
     fdd = None if fd is None else fd.to(dev)
     rows = list(range(B)) if per_sample_rows is None else per_sample_rows
@@ -147,7 +147,7 @@ def _run_config(tag, preset_name, B, T, n_new, keep_rate, fd, quirk, per_sample_
     keep_frac, keep_near = _tie_aware_keep_agreement(reco["vision_logits"], keep_ref, nat_keep)
     vl_err = ((rec_nat["vision_logits"][sub] if ragged else rec_nat["vision_logits"]).float() - reco["vision_logits"].float()).abs().max().item()
     vl_scale = reco["vision_logits"].float().abs().max().item()
-    row = dict(config=tag, preset=preset_name, B=B, T=T, n_new=n_new, keep_rate=keep_rate, mode="reference_batched_quirk" if quirk else
+    row = dict(config=tag, preset=preset_name, dtype=str(dtype).replace("torch.", ""), B=B, T=T, n_new=n_new, keep_rate=keep_rate, mode="reference_batched_quirk" if quirk else
                ("b1" if B == 1 else f"ragged (rows {rows} vs per-sample oracle)"), weights="independent N(0,0.02) per tensor (device_state_dict)",
                err_vs_oracle_bf16=err16, err_vs_oracle_fp32=err32, oracle_floor_bf16_vs_fp32=floor, logit_scale=scale,
                literal_1e2_abs_holds=bool(err32 <= 1e-2), rel_err_fp32=err32 / scale, teacher_forced_argmax_agreement=agree,
@@ -210,6 +210,15 @@ def test_config2_full_size_7b_ragged_vs_per_sample_oracle():
     those samples run alone through the oracle, all 128 tokens"""
     fd = forced_text_decisions(127, 8, keep_rate=0.5, seed=3)
     _run_config("2 (ragged default)", "llava-1.5-7b", 8, 32, 128, 0.2, fd, quirk=False, per_sample_rows=[0, 7])
+
+
+@pytest.mark.timeout(900)
+def test_config2_full_size_7b_float16_vs_oracle():
+    """BASELINE config 2's shape in float16 — the dtype the reference's eval drivers load (dynamic_llava_builder.py:62) — through
+    libdynllava_b200_f16.so: B = 8, reference batched semantics, 32 tokens.  (err_vs_oracle_bf16 / floor in the row are the 16-bit
+    oracle's, here float16.)"""
+    fd = forced_text_decisions(31, 8, keep_rate=0.5, seed=3)
+    _run_config("2 (float16, reference batched semantics)", "llava-1.5-7b", 8, 32, 32, 0.2, fd, quirk=True, dtype=torch.float16)
 
 
 @pytest.mark.timeout(900)

@@ -151,10 +151,13 @@ def test_load_pretrained_model_roundtrip(tmp_path):
     cj.update(mm_vision_tower=str(tower), mm_projector_type="mlp2x_gelu", model_type="dynamic_llava_llama")
     json.dump(cj, open(ck / "config.json", "w"))
     with pytest.warns(UserWarning, match="tokenizer"):
-        tok, model, proc, ctx = load_pretrained_model(str(ck), None, "dynamic-llava-toy", device="cpu")
+        tok, model, proc, ctx = load_pretrained_model(str(ck), None, "dynamic-llava-toy", device="cpu", torch_dtype=torch.bfloat16)
     assert tok is None and ctx == 2048 and proc is not None
     got = model.state_dict()
     assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    with pytest.warns(UserWarning, match="tokenizer"):  # the reference's default dtype (dynamic_llava_builder.py:62)
+        m16 = load_pretrained_model(str(ck), None, "dynamic-llava-toy", device="cpu")[1]
+    assert m16.dtype == torch.float16 and all(torch.equal(v, sd[k].to(torch.float16)) for k, v in m16.state_dict().items())
     assert model.config.sparse_config["sparse_layer"] == 2 and model.get_vision_tower().is_loaded
     with pytest.raises(NotImplementedError):
         load_pretrained_model(str(ck), None, "dynamic-llava-toy", load_4bit=True)
@@ -329,7 +332,7 @@ def test_reference_written_checkpoint_loads(tmp_path):
     assert cj["model_type"] == "dynamic_llava_llama" and "sparse_config" in cj
     from llava.model.dynamic_llava_builder import load_pretrained_model
     with pytest.warns(UserWarning, match="tokenizer"):
-        tok, model, proc, ctx = load_pretrained_model(ck, None, "dynamic-llava-toy", device="cpu")
+        tok, model, proc, ctx = load_pretrained_model(ck, None, "dynamic-llava-toy", device="cpu", torch_dtype=torch.bfloat16)
     cfg = preset("toy")
     cfg["sparse_config"]["use_output_text_predictor"] = True
     sd = {k: v.to(torch.bfloat16) for k, v in numpy_state_dict(cfg, 0).items()}
@@ -362,8 +365,8 @@ def test_eval_driver_import_surface():
 def test_auto_classes_registered_and_from_pretrained(tmp_path):
     """the reference registers its classes with transformers' Auto factories at import time (dynamic_llava_llama.py:172-173) and its
     builder loads through `DynamicLlavaLlamaForCausalLM.from_pretrained(path, low_cpu_mem_usage=True, torch_dtype=float16, ...)`
-    (dynamic_llava_builder.py:62, :191-193): both entry points exist here and return the same weights; float16 is served in bf16 with a
-    warning, anything else is refused"""
+    (dynamic_llava_builder.py:62, :191-193): both entry points exist here and return the same weights; bfloat16 (default) and float16 each have a
+    kernel library, anything else is refused"""
     import json
     from safetensors.torch import save_file
     from transformers import AutoConfig, AutoModelForCausalLM
@@ -386,11 +389,10 @@ def test_auto_classes_registered_and_from_pretrained(tmp_path):
     assert hf_cfg.sparse_config["sparse_layer"] == cfg["sparse_config"]["sparse_layer"]
     m1 = AutoModelForCausalLM.from_pretrained(str(ck), device_map="cpu")
     assert isinstance(m1, DynamicLlavaLlamaForCausalLM)
-    with pytest.warns(UserWarning, match="float16"):
-        m2 = DynamicLlavaLlamaForCausalLM.from_pretrained(str(ck), low_cpu_mem_usage=True, device_map="cpu", torch_dtype=torch.float16)
-    for m in (m1, m2):
+    m2 = DynamicLlavaLlamaForCausalLM.from_pretrained(str(ck), low_cpu_mem_usage=True, device_map="cpu", torch_dtype=torch.float16)
+    for m, dt in ((m1, torch.bfloat16), (m2, torch.float16)):
         got = m.state_dict()
-        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
-        assert m.dtype == torch.bfloat16 and m.config.sparse_config == cfg["sparse_config"]
-    with pytest.raises(NotImplementedError, match="bfloat16 only"):
+        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k].to(dt)) for k in sd)
+        assert m.dtype == dt and m.config.sparse_config == cfg["sparse_config"]
+    with pytest.raises(NotImplementedError, match="bfloat16 or float16 only"):
         DynamicLlavaLlamaForCausalLM.from_pretrained(str(ck), device_map="cpu", torch_dtype=torch.float32)

@@ -7,6 +7,7 @@ attention / GEMM outputs are compared against an fp32 evaluation of the same bf1
 """
 import ctypes
 import math
+import os
 
 import pytest
 import torch
@@ -17,13 +18,15 @@ from oracle import dynllava_oracle as O
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
-BF = torch.bfloat16
+# element type under test: bfloat16 by default; tests/test_fp16_gpu.py re-runs this file with DLB200_TEST_DTYPE=float16 against
+# libdynllava_b200_f16.so (the oracle then runs in float16 too, which is what the reference's eval drivers load)
+BF = getattr(torch, os.environ.get("DLB200_TEST_DTYPE", "bfloat16"))
 
 
 @pytest.fixture(scope="module")
 def L():
     from dynamic_llava_b200._lib import lib
-    lb = lib()
+    lb = lib(BF)
     assert torch.cuda.is_available() and lb.device_is_sm100() == 1
     return lb
 
@@ -64,11 +67,16 @@ def ulp_close(a, b, max_frac=0.005, abs_ok=0.0):
     a, b = a.cpu(), b.cpu()
     if torch.equal(a, b):
         return True
+    max_ulp = 1
+    if BF == torch.float16:
+        # a float16 ulp is 8x smaller than a bfloat16 one, so the same fp32 reduction-order noise flips 8x as many last places, and a
+        # flipped intermediate that is then scaled into a lower binade (RMSNorm's `weight * x_normed`) shows up as 2 ulp
+        max_frac, max_ulp = 8 * max_frac, 2
     ai, bi = a.view(torch.int16).int(), b.view(torch.int16).int()
     d = (ai - bi).abs()
     d[(a.float() - b.float()).abs() <= abs_ok] = 0
     frac = (d > 0).float().mean().item()
-    assert d.max().item() <= 1, f"max ulp diff {d.max().item()}"
+    assert d.max().item() <= max_ulp, f"max ulp diff {d.max().item()}"
     assert frac <= max_frac, f"{frac:.4%} elements differ"
     return True
 
@@ -899,7 +907,9 @@ def test_linear_swiglu_epilogue(L, M, I, K, stream_k):
         assert ((da - dr).abs() <= 0.03 * dr.abs() + 2e-3).all()
         assert (da != dr).float().mean().item() < 0.02
     else:
-        assert torch.equal(act, ref), (act.float() - ref.float()).abs().max()
+        # same rounded gate / up on both sides; the epilogue's sigmoid uses the fast exp (a few fp32 ulps from expf), which can flip a
+        # last place of the 16-bit product: never seen in bf16 on these shapes, ~1e-4 of the elements in fp16
+        ulp_close(act, ref, max_frac=1e-4)
     g32 = x.float() @ w.float().T
     want = (F.silu(g32[:, :I].to(BF)) * g32[:, I:].to(BF)).float()
     assert (act.float().cpu() - want).abs().max() < 2e-2 * max(1.0, want.abs().max().item())

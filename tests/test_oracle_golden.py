@@ -12,7 +12,7 @@ from dynamic_llava_b200.synthetic import numpy_state_dict, synthetic_inputs
 from oracle import dynllava_oracle as O
 
 CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "toy_*.pt")))
-DT = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}
+DT = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16, "torch.float16": torch.float16}
 
 
 def _load(golden_dir, name):
