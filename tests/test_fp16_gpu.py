@@ -76,10 +76,11 @@ def test_generate_against_reference_fp16_fixture(name):
 
 
 def test_gpu_suites_pass_in_float16():
-    """re-run the per-kernel and model-level GPU tests with every tensor, the library and the oracle in float16"""
+    """re-run the per-kernel, model-level and random-sweep GPU tests with every tensor, the library and the oracle in float16"""
     env = dict(os.environ, DLB200_TEST_DTYPE="float16")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k", "not full_size", "-p", "no:cacheprovider",
-                        os.path.join(ROOT, "tests", "test_kernels_gpu.py"), os.path.join(ROOT, "tests", "test_model_gpu.py")],
+                        os.path.join(ROOT, "tests", "test_kernels_gpu.py"), os.path.join(ROOT, "tests", "test_model_gpu.py"),
+                        os.path.join(ROOT, "tests", "test_fuzz_gpu.py")],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = r.stdout[-3000:] + r.stderr[-1500:]
     assert r.returncode == 0, tail

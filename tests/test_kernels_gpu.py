@@ -818,6 +818,33 @@ def test_linear_2cta_tcgen05(L, M, N, K, act, bias, res, stream_k):
         ulp_close(out, lib.cpu(), max_frac=0.02, abs_ok=2e-3)
 
 
+@pytest.mark.parametrize("seed", range(40))
+def test_linear_random_shapes(L, seed):
+    """seeded random (M, N, K, epilogue) sweep of dl_linear with the stream-K workspace supplied, so the launcher's own heuristic picks
+    the schedule: unaligned M, N down to 8, one to forty k-blocks, every epilogue"""
+    import numpy as np
+    r = np.random.Generator(np.random.PCG64(500 + seed))
+    M = int(r.choice([int(r.integers(1, 64)), int(r.integers(64, 600)), int(r.integers(600, 2600))]))
+    N = 8 * int(r.choice([int(r.integers(1, 16)), int(r.integers(16, 200)), int(r.integers(200, 700))]))
+    K = 64 * int(r.integers(1, 41))
+    act = int(r.integers(0, 3))
+    bias = bool(r.integers(0, 2))
+    res = act == 0 and bool(r.integers(0, 2))
+    x, w = rnd(M, K, seed=seed).to(DEV), rnd(N, K, seed=seed + 1, scale=0.05).to(DEV)
+    b = rnd(N, seed=seed + 2, scale=0.1).to(DEV) if bias else None
+    rr = rnd(M, N, seed=seed + 3).to(DEV) if res else None
+    ws = _linear_ws(L)
+    out = rr.clone() if res else torch.full((M, N), float("nan"), device=DEV, dtype=BF)
+    L.linear(P(x), P(w), P(b), P(out) if res else None, P(out), M, N, K, act, P(ws), ST())
+    torch.cuda.synchronize()
+    assert int(ws.view(torch.int32)[_linear_ws_flag_offset(L):].abs().sum()) == 0
+    ref = _linear_ref(x, w, b, act, rr).float()
+    got = out.float()
+    assert torch.isfinite(got).all(), (M, N, K, act, bias, res)
+    tol = 1.5e-2 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() < tol, (M, N, K, act, bias, res, (got - ref).abs().max().item(), tol)
+
+
 def test_linear_repeated_launches_and_determinism(L):
     """persistent pairs + double-buffered TMEM: many tiles per pair, launched repeatedly on one stream, bit-identical every time"""
     M, N, K = 4856, 4096, 1024
