@@ -462,6 +462,16 @@ def test_attn_decode(L, lens, n_split, quirk):
             assert (got - ref).abs().max() < 2e-2 * max(1.0, ref.abs().max()), (b, h, (got - ref).abs().max())
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_attn_decode_random_lengths(L, seed):
+    """seeded random ragged lengths (0 .. 2100 keys per sample, up to 8 samples), every split count, both batching semantics"""
+    import numpy as np
+    r = np.random.Generator(np.random.PCG64(700 + seed))
+    B = int(r.integers(1, 9))
+    lens = [int(r.choice([0, 1, int(r.integers(2, 130)), int(r.integers(130, 2100))])) for _ in range(B)]
+    test_attn_decode(L, lens, int(r.choice([1, 2, 3, 4, 8, 16])), int(r.integers(0, 2)))
+
+
 @pytest.mark.parametrize("lens,n_split,S,quirk", [([146, 210, 64, 1], 1, 3, 0), ([735, 650, 129, 300], 2, 2, 0), ([40, 70, 70, 3], 1, 1, 1)])
 def test_attn_decode_fused_equals_unfused(L, lens, n_split, S, quirk):
     """dl_attn_decode_fused (reduce + RoPE + append inside the attention CTA) must be bit-identical to
@@ -550,6 +560,17 @@ def test_attn_prefill_tc4_persistent(L, q_lens, pasts, flags):
     """K2 v4 (persistent): 64-key half tiles, two S buffers per group; flags=1 evaluates a quarter of the exp2 with the FMA
     polynomial."""
     _varlen_case(L, _call_tc4(L, flags), 128, True, q_lens, pasts, nh=2)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_attn_prefill_tc4_random_ragged(L, seed):
+    """seeded random ragged batches: 1-6 samples, 1-700 query rows each, 0-600 cached rows each (second-turn shape), both exp2 modes"""
+    import numpy as np
+    r = np.random.Generator(np.random.PCG64(800 + seed))
+    B = int(r.integers(1, 7))
+    q_lens = [int(r.choice([1, int(r.integers(2, 130)), int(r.integers(130, 700))])) for _ in range(B)]
+    pasts = [int(r.choice([0, 0, int(r.integers(1, 600))])) for _ in range(B)]
+    _varlen_case(L, _call_tc4(L, int(r.integers(0, 2))), 128, True, q_lens, pasts, nh=int(r.integers(1, 4)))
 
 
 @pytest.mark.parametrize("B,nh,Lq,Lk", [(2, 4, 300, 300), (1, 2, 64, 200), (3, 2, 129, 129)])
@@ -724,6 +745,21 @@ def test_skinny_gemm_tcgen05(L, M, N, K, splits):
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), err  # fp32 accumulation of exact bf16 products
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_skinny_gemm_random_shapes(L, seed):
+    """seeded random decode-GEMM shapes: 1-64 rows, N any multiple of 8, 1-172 k-blocks, split count from the launcher's own heuristic
+    or forced"""
+    import numpy as np
+    r = np.random.Generator(np.random.PCG64(900 + seed))
+    M = int(r.integers(1, 65))
+    N = 8 * int(r.choice([int(r.integers(1, 64)), int(r.integers(64, 4000))]))
+    K = 64 * int(r.choice([int(r.integers(1, 9)), int(r.integers(9, 173))]))
+    kb = K // 64
+    splits = int(r.choice([1, L.skinny_gemm_splits(N, K, 296), int(r.integers(1, min(kb, 16) + 1))]))
+    splits = max(1, min(splits, kb))
+    test_skinny_gemm_tcgen05(L, M, N, K, splits)
 
 
 @pytest.mark.parametrize("M,I,K", [(8, 512, 256), (8, 11008, 4096), (3, 13824, 5120), (24, 1024, 512)])
