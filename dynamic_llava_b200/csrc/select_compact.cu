@@ -4,10 +4,12 @@
 // keep = ascending indices of the k best scores, hidden' = [left | image[keep] | right], RoPE positions stay the
 // ORIGINAL (pre-drop) positions, and a CSR header (cu_seqlens) describes the packed result.
 //
-// Grid = (R, B).  Every CTA of sample b redoes the selection for its sample in shared memory — an O(n) two-pass radix
-// select on the 16-bit score keys (256-bin histogram of the high byte, then of the low byte inside the boundary bin,
-// warp-aggregated with match.any so equal keys cost one shared atomic per warp), followed by an ordered compaction
-// scan; replicating it per CTA is cheaper than a second kernel or a round trip of the index map through HBM.
+// Grid = (R, B).  Every CTA of sample b redoes the selection for its sample: ONE selection thread per image token holds that
+// token's 16-bit score key in a register, the k-th largest key is found by a 16-step bitwise search in which every step is a
+// single counting barrier (`bar.red.popc` on the selection threads' named barrier: count(key >= candidate) in one instruction, no
+// shared-memory histogram, no atomics), one more count gives #keys above it, and an ordered compaction (warp ballots + the
+// per-warp totals) writes the ascending index list.  ~20 barriers of ~50 cycles: well under a microsecond, so replicating it per
+// CTA is cheaper than a second kernel or a round trip of the index map through HBM.
 // The rows move through a shared-memory ring of whole-row slots driven by ONE thread (warp 0) with bulk async copies
 // (cp.async.bulk global->shared on an mbarrier, shared->global in bulk groups): no register staging, 64 KB in flight per
 // CTA.  Rows are visited text-first: the [left | right] text rows do not depend on the selection, so the copy thread streams
@@ -18,9 +20,8 @@
 #include "common.cuh"
 #include "../../include/dynllava_b200.h"
 
-#define SC_THREADS 256           // selection threads (warps 1-8)
-#define SC_BLOCK (SC_THREADS + 32)  // + warp 0: the copy engine driver
 #define SC_MAX_IMG 1024
+#define SC_MAX_BLOCK (SC_MAX_IMG + 32)  // one selection thread per image token (rounded up to whole warps) + warp 0: the copy engine driver
 #define SC_MAX_SLOTS 16
 #define SC_RING_BYTES 65536
 
@@ -35,18 +36,24 @@ DL_DEVINL void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// histogram update where lanes holding the same bin share one shared-memory atomic
-DL_DEVINL void hist_add_aggregated(int* hist, int bin, bool valid) {
-  const unsigned act = __ballot_sync(0xffffffffu, valid);
-  if (valid) {
-    const unsigned peers = __match_any_sync(act, bin);
-    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
-  }
+// barrier 1 = the selection threads only (n_sel of them: whole warps).  sel_count: block-wide popcount of a predicate in ONE
+// barrier instruction; every thread gets the same total.
+DL_DEVINL void sel_sync(int n_sel) { asm volatile("bar.sync 1, %0;" ::"r"(n_sel) : "memory"); }
+DL_DEVINL int sel_count(int n_sel, bool pred) {
+  int c;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.s32 p, %2, 0;\n"
+      "bar.red.popc.u32 %0, 1, %1, p;\n"
+      "}"
+      : "=r"(c)
+      : "r"(n_sel), "r"((int)pred)
+      : "memory");
+  return c;
 }
 
-DL_DEVINL void sel_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the selection threads only
-
-__global__ void __launch_bounds__(SC_BLOCK) select_compact_kernel(
+__global__ void __launch_bounds__(SC_MAX_BLOCK) select_compact_kernel(
     const bf16* __restrict__ logits,         // [B, n_img, 2]
     const int64_t* __restrict__ forced_keep, // [B, k] or null
     const bf16* __restrict__ hid_in,         // [B, P, H]
@@ -57,14 +64,12 @@ __global__ void __launch_bounds__(SC_BLOCK) select_compact_kernel(
     int P, int H, int s0, int n_img, int k, int n_slots) {
   extern __shared__ __align__(128) uint8_t ring[];  // n_slots whole rows
   __shared__ __align__(8) uint64_t full[SC_MAX_SLOTS];
-  __shared__ __align__(8) uint64_t sel_done;  // count SC_THREADS: kidx[] is final
-  __shared__ uint16_t key[SC_MAX_IMG];
+  __shared__ __align__(8) uint64_t sel_done;  // count 1: kidx[] is final (one arrival after the selection threads' last barrier)
   __shared__ int16_t kidx[SC_MAX_IMG];
-  __shared__ int hist[256];
-  __shared__ int wsum[SC_THREADS / 32];
-  __shared__ int sel[4];  // [0] boundary bin, [1] #keys above it
+  __shared__ int wsum[SC_MAX_IMG / 32];
   const int b = blockIdx.y;
-  const int tid = (int)threadIdx.x - 32;  // selection thread index; warp 0 (tid < 0) drives the copies
+  const int tid = (int)threadIdx.x - 32;  // selection thread index == image token index; warp 0 (tid < 0) drives the copies
+  const int n_sel = (int)blockDim.x - 32;  // n_img rounded up to whole warps
   const int R = gridDim.x, r = blockIdx.x;
   const int Pp = P - n_img + k;
   const int n_text = Pp - k;
@@ -78,10 +83,14 @@ __global__ void __launch_bounds__(SC_BLOCK) select_compact_kernel(
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_slots; ++s) mbar_init(&full[s], 1);
-    mbar_init(&sel_done, SC_THREADS);
+    mbar_init(&sel_done, 1);
     fence_barrier_init();
   }
   __syncthreads();
+  // launched with the programmatic-serialization attribute: the block is resident and its barriers are initialised while the
+  // producer of `logits` / `hid_in` (the predictor's last Linear) is still draining; nothing of the predecessor is read above
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     // ---- copy engine: ring of whole-row slots, loads n_slots - 1 deep, stores in bulk groups.  It never takes part in the
@@ -119,96 +128,53 @@ __global__ void __launch_bounds__(SC_BLOCK) select_compact_kernel(
   if (tid < 0) return;  // the rest of warp 0
 
   if (forced_keep != nullptr) {
-    for (int i = tid; i < k; i += SC_THREADS) kidx[i] = (int16_t)forced_keep[(int64_t)b * k + i];
+    for (int i = tid; i < k; i += n_sel) kidx[i] = (int16_t)forced_keep[(int64_t)b * k + i];
   } else if (k == n_img) {  // keep rate 1.0: the ascending indices of ALL tokens, whatever the scores
-    for (int i = tid; i < k; i += SC_THREADS) kidx[i] = (int16_t)i;
+    for (int i = tid; i < k; i += n_sel) kidx[i] = (int16_t)i;
   } else if (k > 0) {
-    // scores rounded where the reference's bf16 log_softmax rounds, mapped to order-preserving 16-bit keys
-    for (int i = tid; i < n_img; i += SC_THREADS) {
-      const bf16x2 l = *reinterpret_cast<const bf16x2*>(logits + ((int64_t)b * n_img + i) * 2);
-      const float l0 = __low2float(l), l1 = __high2float(l);
-      const float m = fmaxf(l0, l1);
-      const bf16 sc = f2bf((l0 - m) - logf(expf(l0 - m) + expf(l1 - m)));
+    // this thread's token: score rounded where the reference's 16-bit log_softmax rounds, mapped to an order-preserving 16-bit key
+    const bool valid = tid < n_img;
+    uint32_t key = 0;
+    if (valid) {
+      const bf16x2 l = *reinterpret_cast<const bf16x2*>(logits + ((int64_t)b * n_img + tid) * 2);
+      const float2 lf = bf2f2(l);
+      const float m = fmaxf(lf.x, lf.y);
+      const bf16 sc = f2bf((lf.x - m) - logf(expf(lf.x - m) + expf(lf.y - m)));
       uint16_t bits = *reinterpret_cast<const uint16_t*>(&sc);
       if (bits == 0x8000u) bits = 0;  // -0 == +0
-      key[i] = (bits & 0x8000u) ? (uint16_t)~bits : (uint16_t)(bits | 0x8000u);
+      key = (bits & 0x8000u) ? (uint16_t)~bits : (uint16_t)(bits | 0x8000u);
     }
-    // two radix passes: find T = the k-th largest key, c_gt = #keys > T
-    int prefix = 0, c_gt = 0, want = k;
-    const int n_round = (n_img + SC_THREADS - 1) / SC_THREADS * SC_THREADS;
-    for (int pass = 0; pass < 2; ++pass) {
-      if (tid < 256) hist[tid] = 0;
-      sel_sync();
-      for (int i = tid; i < n_round; i += SC_THREADS) {  // whole warps stay converged for match.any
-        const int kk = i < n_img ? key[i] : 0;
-        if (pass == 0)
-          hist_add_aggregated(hist, kk >> 8, i < n_img);
-        else
-          hist_add_aggregated(hist, kk & 255, i < n_img && (kk >> 8) == prefix);
-      }
-      sel_sync();
-      if (tid < 32) {  // suffix scan over the 256 bins (8 per lane), locate the bin that holds the `want`-th largest
-        int loc = 0;
+    // T = the k-th largest key = the largest T with count(key >= T) >= k, built bit by bit from the top
+    uint32_t T = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) loc += hist[tid * 8 + j];
-        int inc = loc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_down_sync(0xffffffffu, inc, o);
-          if (tid + o < 32) inc += t;
-        }
-        int run = inc - loc;  // keys in bins above this lane's 8
-        for (int j = 7; j >= 0; --j) {
-          const int h = hist[tid * 8 + j];
-          if (run < want && want <= run + h) {
-            sel[0] = tid * 8 + j;
-            sel[1] = run;
-          }
-          run += h;
-        }
-      }
-      sel_sync();
-      if (pass == 0) prefix = sel[0];
-      c_gt += sel[1];
-      want -= sel[1];
-      if (pass == 1) prefix = (prefix << 8) | sel[0];
-      sel_sync();
+    for (int bit = 15; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      if (sel_count(n_sel, valid && key >= cand) >= k) T = cand;
     }
-    const int T = prefix, need_eq = k - c_gt;
-    // ordered compaction: contiguous chunk per thread, block exclusive scan of (#gt, #eq) packed in one int
-    const int per = (n_img + SC_THREADS - 1) / SC_THREADS;
-    const int lo = tid * per, hi = min(lo + per, n_img);
-    int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += (key[i] > T) + ((key[i] == T) << 16);
-    int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((tid & 31) >= o) inc += t;
-    }
-    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
-    sel_sync();
+    const bool gt = valid && key > T, eq = valid && key == T;
+    const int need_eq = k - sel_count(n_sel, gt);
+    // ordered compaction: exclusive (#gt, #eq) before this token = lanes below in the warp + the warps before
+    const unsigned m_gt = __ballot_sync(0xffffffffu, gt), m_eq = __ballot_sync(0xffffffffu, eq);
+    const unsigned below = (1u << (tid & 31)) - 1u;
+    if ((tid & 31) == 0) wsum[tid >> 5] = __popc(m_gt) | (__popc(m_eq) << 16);
+    sel_sync(n_sel);
     int base = 0;
     for (int w = 0; w < (tid >> 5); ++w) base += wsum[w];
-    const int excl = base + inc - cnt;
-    int gt_before = excl & 0xffff, eq_before = excl >> 16;
-    for (int i = lo; i < hi; ++i) {
-      const int kk = key[i];
-      if (kk > T) {
-        kidx[gt_before + min(eq_before, need_eq)] = (int16_t)i;
-        ++gt_before;
-      } else if (kk == T) {
-        if (eq_before < need_eq) kidx[gt_before + eq_before] = (int16_t)i;
-        ++eq_before;
-      }
-    }
+    const int gt_before = (base & 0xffff) + __popc(m_gt & below), eq_before = (base >> 16) + __popc(m_eq & below);
+    // ties at the k-th score go to the lower index (= stable descending sort): the first need_eq equal keys are kept
+    if (gt)
+      kidx[gt_before + min(eq_before, need_eq)] = (int16_t)tid;
+    else if (eq && eq_before < need_eq)
+      kidx[gt_before + eq_before] = (int16_t)tid;
   }
-  sel_sync();
+  sel_sync(n_sel);
 
-  mbar_arrive(&sel_done);  // release: kidx[] is visible to the copy thread's acquire
+  // ONE arrival (hundreds of arrivals on one mbarrier word would serialise): the named barrier above ordered every selection
+  // thread's kidx[] writes before this release, the copy thread's wait is the acquire
+  if (tid == 0) mbar_arrive(&sel_done);
   if (r == 0) {  // index map + CSR header
-    for (int i = tid; i < k; i += SC_THREADS) keep_index[(int64_t)b * k + i] = kidx[i];
-    for (int j = tid; j < Pp; j += SC_THREADS) {
+    for (int i = tid; i < k; i += n_sel) keep_index[(int64_t)b * k + i] = kidx[i];
+    for (int j = tid; j < Pp; j += n_sel) {
       int p = j < s0 ? j : (j < s0 + k ? s0 + kidx[j - s0] : j + (n_img - k));
       pos_out[(int64_t)b * Pp + j] = p;
     }
@@ -241,15 +207,17 @@ extern "C" int dl_select_compact(const void* logits, const int64_t* forced_keep,
   int R = ctas_per_sample;
   if (R <= 0) {
     // measured (tools/k1_sweep.py): text rows stream best in short CTAs (~10 rows each; more, shorter CTAs also even out the
-    // tail), image rows in long ones (every CTA repeats the ~3 us select before its first image row)
+    // tail), image rows in long ones (every CTA repeats the ~1 us select before its first image row)
     const int n_free = (k == n_img && forced_keep == nullptr) ? Pp : Pp - k;  // rows whose source is known without the select
     R = (n_free + 9) / 10 + (Pp - n_free + 71) / 72;
-    if (R * B < 148) R = (148 + B - 1) / B;  // small problems: at least one CTA per SM
+    if (R * B < 148) R = B <= 148 ? 148 / B : 1;  // small problems: one CTA per SM (never a second, partial wave)
   }
   if (R > Pp) R = Pp;
   if (R < 1) R = 1;
-  select_compact_kernel<<<dim3(R, B), SC_BLOCK, smem, stream>>>((const bf16*)logits, forced_keep, (const bf16*)hidden_in,
-                                                                  (bf16*)hidden_out, keep_index, pos_out, cu_seqlens, P, H,
-                                                                  img_start, n_img, k, n_slots);
+  const int n_sel = n_img > 0 ? (n_img + 31) / 32 * 32 : 32;  // one selection thread per image token, whole warps
+  cudaError_t le = dl_launch_pdl(select_compact_kernel, dim3(R, B), dim3(32 + n_sel), (size_t)smem, stream, (const bf16*)logits,
+                                 forced_keep, (const bf16*)hidden_in, (bf16*)hidden_out, keep_index, pos_out, cu_seqlens, P, H,
+                                 img_start, n_img, k, n_slots);
+  if (le != cudaSuccess) return dl_set_error((int)le, "dl_select_compact(launch)");
   DL_CHECK_LAUNCH("dl_select_compact");
 }
