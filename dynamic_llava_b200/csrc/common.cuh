@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 // Element type of this build.  The same sources are compiled twice: libdynllava_b200.so computes in bfloat16 (default)
 // and libdynllava_b200_f16.so (-DDL_HALF) in float16, the dtype the reference's eval drivers load
@@ -49,6 +50,19 @@ extern "C" int dl_set_error(int code, const char* where);
 DL_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 DL_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// debugging aid: DLB200_NO_PDL=<bitmask> launches kernels fully serialised (their griddepcontrol instructions become no-ops):
+// 1 = every dl_launch_pdl user, 2 = the prefill GEMM (gemm2), 4 = the many-row norm kernels, 8 = K1
+static inline int dl_pdl_mask() {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("DLB200_NO_PDL");
+    mask = e != nullptr ? atoi(e) : 0;
+  }
+  return mask;
+}
+static inline int dl_pdl_enabled(int site_bit = 0) { return (dl_pdl_mask() & (1 | site_bit)) == 0 || (site_bit == 2 && (dl_pdl_mask() & 2) == 0) ? 1 : 0; }
+static thread_local int dl_pdl_site = 0;  // call sites that can be switched off separately set this right before dl_launch_pdl
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t dl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                         Args... args) {
@@ -59,7 +73,8 @@ static inline cudaError_t dl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = dl_pdl_enabled(dl_pdl_site);
+  dl_pdl_site = 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -94,6 +94,7 @@ extern "C" int dl_rmsnorm(const void* x, const void* w, void* y, int rows, int H
     const dim3 grid((rows + 7) / 8), block(256);
 #define DL_RMS_ROWS(CH_)                                                                                                          \
   case CH_:                                                                                                                       \
+    dl_pdl_site = 4;                                                                                                              \
     dl_launch_pdl(rmsnorm_rows_kernel<CH_>, grid, block, 0, stream, (const bf16*)x, (const bf16*)w, (bf16*)y, rows, H, eps); \
     DL_CHECK_LAUNCH("dl_rmsnorm");
     switch (H / 256) {
@@ -212,6 +213,7 @@ extern "C" int dl_layernorm(const void* x, const void* w, const void* b, void* y
     const dim3 grid((rows + 7) / 8), block(256);
 #define DL_LN_ROWS(CH_)                                                                                                              \
   case CH_:                                                                                                                          \
+    dl_pdl_site = 4;                                                                                                              \
     dl_launch_pdl(layernorm_rows_kernel<CH_>, grid, block, 0, stream, (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, rows, H, \
                   eps);                                                                                                              \
     DL_CHECK_LAUNCH("dl_layernorm");

@@ -287,6 +287,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       }
 
       const bool gather = kb1 < KB;  // the tile's remaining k-blocks were computed (first thing) by the following pairs
+      // The workspace is shared by every dl_linear launch of the stream, and this kernel is launched with programmatic
+      // serialization: its CTAs can be resident while the PREVIOUS GEMM's pairs are still parking and gathering through the same
+      // slots and flags.  Only the producer thread executes griddepcontrol.wait, so nothing of the workspace may be touched before
+      // this warp has observed its own accumulator (tmem_full <- MMA <- TMA <- the producer's wait): polling the flags first let an
+      // early-resident finisher consume the previous launch's flags (wrong sums on shapes where both launches are cut, e.g. M = 292).
+      mbar_wait(&S.tmem_full[a], (sc >> 1) & 1);
+      tc_fence_after();
       if (gather) {
         // wait until this warp's counterpart in every contributing pair has parked its slice
         if (lane == 0) {
@@ -300,8 +307,6 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         }
         __syncwarp();
       }
-      mbar_wait(&S.tmem_full[a], (sc >> 1) & 1);
-      tc_fence_after();
 #pragma unroll 1
       for (int c = hh; c < OUT_W / 64; c += 2) {
         const int col0 = col_t + c * 64;
@@ -523,7 +528,7 @@ static int g2_launch(const void* x, const void* w, const void* bias, const void*
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].val.programmaticStreamSerializationAllowed = dl_pdl_enabled(2);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   cudaError_t le = cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI>, tx, tw, to, (const bf16*)bias, (const bf16*)residual, M, N_out, sc, up_row0,

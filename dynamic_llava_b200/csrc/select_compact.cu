@@ -215,6 +215,7 @@ extern "C" int dl_select_compact(const void* logits, const int64_t* forced_keep,
   if (R > Pp) R = Pp;
   if (R < 1) R = 1;
   const int n_sel = n_img > 0 ? (n_img + 31) / 32 * 32 : 32;  // one selection thread per image token, whole warps
+  dl_pdl_site = 8;
   cudaError_t le = dl_launch_pdl(select_compact_kernel, dim3(R, B), dim3(32 + n_sel), (size_t)smem, stream, (const bf16*)logits,
                                  forced_keep, (const bf16*)hidden_in, (bf16*)hidden_out, keep_index, pos_out, cu_seqlens, P, H,
                                  img_start, n_img, k, n_slots);

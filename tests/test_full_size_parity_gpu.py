@@ -222,6 +222,16 @@ def test_config2_full_size_7b_float16_vs_oracle():
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("B", [2, 3, 5])
+def test_full_size_7b_batch_sizes_outside_the_baseline_configs(B):
+    """B = 2 and 3 give 292 / 438 rows in layers >= 2: every GEMM of the layer is cut by stream-K, which exposed a cross-launch race on
+    the shared workspace that the BASELINE batch sizes (4, 8, 16) never hit (tests/test_kernels_gpu.py::
+    test_linear_back_to_back_launches_share_the_stream_k_workspace is the kernel-level regression)."""
+    fd = forced_text_decisions(3, B, keep_rate=0.5, seed=3)
+    _run_config(f"batch-size sweep B={B}", "llava-1.5-7b", B, 32, 4, 0.2, fd, quirk=True)
+
+
+@pytest.mark.timeout(900)
 def test_config3_full_size_7b_per_rank_shape_vs_oracle():
     """BASELINE config 3 per rank: B = 8, 256 tokens, per-sample forced keep rates linspace(0.1, 0.9, 8) (ragged-KV stress), reference
     batched semantics"""

@@ -900,6 +900,64 @@ def test_linear_repeated_launches_and_determinism(L):
         assert (outs[0].float() - ref).abs().max() < 1.5e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("B", [2, 3])
+def test_linear_back_to_back_launches_share_the_stream_k_workspace(L, B):
+    """regression (found at full 7B size with B = 2 / 3, never at the BASELINE batch sizes): dl_linear is launched with programmatic
+    serialization and every launch of a stream shares one stream-K workspace, so the CTAs of launch n+1 can be resident while launch n
+    is still parking / gathering through the same slots and flags; a finisher that polled the flags before observing its own accumulator
+    consumed the previous launch's flags.  The GEMM sequence of 7B decoder layers with B*146 rows — q|k|v, o_proj (+x), RMSNorm,
+    gate|up + SwiGLU, down_proj (+x), RMSNorm, ... — replayed from a CUDA graph (no host gaps between the launches) must equal the same
+    sequence with a sync after every launch, bit for bit."""
+    M, H, I = B * 146, 4096, 11008
+    x0 = rnd(M, H, seed=180)
+    wq, wo = rnd(3 * H, H, seed=181, scale=0.02).to(DEV), rnd(H, H, seed=182, scale=0.02).to(DEV)
+    wgu, wd = rnd(2 * I, H, seed=183, scale=0.02).to(DEV), rnd(H, I, seed=184, scale=0.02).to(DEV)
+    nw = torch.ones(H, dtype=BF, device=DEV)
+    ws = _linear_ws(L)
+    n_layers = 6
+
+    def layers(x, sync):
+        outs = []
+
+        def step():
+            if sync:
+                torch.cuda.synchronize()
+        for _ in range(n_layers):
+            xn = torch.empty(M, H, device=DEV, dtype=BF)
+            L.rmsnorm(P(x), P(nw), P(xn), M, H, 1e-5, ST()); step()
+            qkv = torch.empty(M, 3 * H, device=DEV, dtype=BF)
+            L.linear(P(xn), P(wq), None, None, P(qkv), M, 3 * H, H, 0, P(ws), ST()); step()
+            attn = qkv[:, 2 * H:].contiguous(); step()  # stands in for the attention output (a torch copy kernel: a normal launch)
+            L.linear(P(attn), P(wo), None, P(x), P(x), M, H, H, 0, P(ws), ST()); step()  # x += o_proj(attn), in place like the engine
+            L.rmsnorm(P(x), P(nw), P(xn), M, H, 1e-5, ST()); step()
+            act = torch.empty(M, I, device=DEV, dtype=BF)
+            L.linear_swiglu(P(xn), P(wgu), P(act), M, I, H, P(ws), ST()); step()
+            L.linear(P(act), P(wd), None, P(x), P(x), M, H, I, 0, P(ws), ST()); step()  # x += down_proj(act)
+            outs += [qkv, act]
+        return outs
+
+    x_ref = x0.to(DEV).clone()
+    ref = layers(x_ref, True)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        x_g = x0.to(DEV).clone()
+        layers(x_g, False)  # warm-up: attribute setup, tensor-map cache
+        x_g.copy_(x0.to(DEV))
+        with torch.cuda.graph(g, stream=side):
+            outs = layers(x_g, False)
+    torch.cuda.current_stream().wait_stream(side)
+    for rep in range(3):
+        x_g.copy_(x0.to(DEV))
+        g.replay()
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(zip([x_g] + outs, [x_ref] + ref)):
+            assert torch.equal(a, b), (rep, i, (a.float() - b.float()).abs().max().item())
+    assert int(ws.view(torch.int32)[_linear_ws_flag_offset(L):].abs().sum()) == 0
+
+
 @pytest.mark.parametrize("M,N,K,res", [(4608, 512, 4096, False), (4, 32000, 5120, False), (8192, 5120, 5120, True), (6348, 5120, 13824, True),
                                        (1168, 4096, 4096, True), (2308, 1024, 4096, True), (4608, 2048, 512, False), (1168, 12288, 4096, False)])
 def test_linear_stream_k_bitwise_repeatable(L, M, N, K, res):
