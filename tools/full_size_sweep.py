@@ -21,7 +21,7 @@ for seed in range(s0, s0 + n):
     Tn = int(r.choice([8, 17, 32, 33, 64, 100, 191, 300, 450]))
     rate = float(r.choice([0.1, 0.2, 0.35, 0.5, 0.77, 1.0]))
     quirk = bool(r.integers(0, 2)) or B == 1
-    n_new = int(r.choice([2, 3, 5]))
+    n_new = int(os.environ.get("SWEEP_N_NEW", r.choice([2, 3, 5])))
     fd = forced_text_decisions(n_new - 1, B, keep_rate=[float(x) for x in r.choice([0.0, 0.3, 0.5, 0.8, 1.0], size=B)], seed=seed)
     rows = None if quirk else sorted(set([0, B - 1]))
     tag = f"sweep {preset_name} seed={seed} B={B} T={Tn} keep={rate} quirk={quirk} n_new={n_new}"
