@@ -250,3 +250,84 @@ def test_config4_full_size_13b_prefill_vs_oracle():
 def test_config5_full_size_7b_keep_half_vs_oracle():
     """one point of BASELINE config 5's sweep: 7B, B = 16, keep 0.5 (k = 288, P' = 319), prefill + 3 tokens, output predictor off"""
     _run_config("5 (keep 0.5 point)", "llava-1.5-7b", 16, 32, 4, 0.5, None, quirk=True)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("B", [1, 2])
+def test_full_size_7b_second_user_turn_vs_oracle(B):
+    """multi-round call pattern of llava/dynamic_eval/model_lvis_multi_round_for_meteor.py:150-185 at full 7B size: prefill -> 3 decode
+    steps -> a 40-token new user turn over the ragged cache (q_len > 1 with past, README.md:110: instruct predictor off, every new token
+    persisted) -> 2 decode steps, forced output decisions on both sides, tokens teacher-forced.  B = 2 runs in the default ragged mode and
+    is compared sample by sample with each sample run alone through the oracle (the batched new-turn form of the reference quirk is
+    de-scoped).  Every call's logits within 2 * floor + 1e-2 * scale of the fp32 oracle, kv_len exact after every call."""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    dev = torch.device("cuda")
+    cfgd = preset("llava-1.5-7b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = True
+    sd16 = device_state_dict(cfgd, seed=0, device=dev)
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device=dev)
+    model.get_vision_tower().load_model()
+    model.load_state_dict(sd16, strict=True)
+    ids, pix = synthetic_inputs(cfgd, B, 32, seed=1)
+    cont, _ = synthetic_inputs(cfgd, B, 41, seed=5)
+    ids, pix, cont = ids.to(dev), pix.to(dev), cont[:, 1:].to(dev).clone()
+    cont[cont < 0] = 7  # no <image> placeholder in the second turn
+    dec = forced_text_decisions(5, B, keep_rate=0.5, seed=11).to(dev)  # [5, B]
+
+    def oracle_calls(sd, pixels, b, keep=None, teacher=None):
+        """-> (list of last-position / all-position logits per call, lens per call, tokens fed, keep_index) for sample b alone"""
+        rec = {}
+        lg, past = O.model_forward(sd, cfgd, ids[b: b + 1], images=pixels[b: b + 1], forced_keep_index=keep, record=rec)
+        outs, lens, toks = [lg[:, -1]], [torch.stack(list(past[1]), 0).clone()], []
+        step = 0
+        for phase, n in (("dec", 3), ("turn", 1), ("dec", 2)):
+            for _ in range(n):
+                if phase == "turn":
+                    lg, past = O.model_forward(sd, cfgd, cont[b: b + 1], past=past)
+                    outs.append(lg[0])
+                else:
+                    nxt = outs[-1][-1:].argmax(-1).reshape(1, 1) if teacher is None else teacher[len(toks)].reshape(1, 1)
+                    toks.append(nxt.reshape(()))
+                    lg, past = O.model_forward(sd, cfgd, nxt, past=past, forced_text_decision=dec[step, b].reshape(1, 1))
+                    outs.append(lg[:, -1])
+                    step += 1
+                lens.append(torch.stack(list(past[1]), 0).clone())
+        return outs, lens, toks, rec["keep_index"]
+
+    o16 = [oracle_calls(sd16, pix, b) for b in range(B)]
+    keep = torch.cat([o[3] for o in o16], 0)
+    toks = torch.stack([torch.stack(o[2]) for o in o16], 0)  # [B, 5]
+    # GPU: the same calls through forward() with the returned cache
+    out = model(ids, images=pix, forced_keep_index=keep)
+    got, glens = [out.logits[:, -1].float().clone()], [torch.stack(list(out.past_key_values[1]), 0).clone()]
+    past, step = out.past_key_values, 0
+    for phase, n in (("dec", 3), ("turn", 1), ("dec", 2)):
+        for _ in range(n):
+            if phase == "turn":
+                out = model(cont, past_key_values=past)
+                got.append(out.logits.float().clone())
+            else:
+                out = model(toks[:, step: step + 1], past_key_values=past, forced_text_decision=dec[step])
+                got.append(out.logits[:, -1].float().clone())
+                step += 1
+            past = out.past_key_values
+            glens.append(torch.stack(list(past[1]), 0).clone())
+    del model, out, past
+    torch.cuda.empty_cache()
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    worst = dict(err32=0.0, floor=0.0, scale=0.0)
+    for b in range(B):
+        o32 = oracle_calls(sd32, pix.float(), b, keep=keep[b: b + 1], teacher=toks[b])
+        for c, (a16, a32) in enumerate(zip(o16[b][0], o32[0])):
+            g = got[c][b]
+            a16, a32 = a16.float().reshape(g.shape), a32.float().reshape(g.shape)
+            floor, scale = (a16 - a32).abs().max().item(), a32.abs().max().item()
+            err = (g - a32).abs().max().item()
+            assert err <= 2 * floor + 1e-2 * scale, (b, c, err, floor, scale)
+            if err > worst["err32"]:
+                worst = dict(err32=err, floor=floor, scale=scale, call=c, sample=b)
+        for c, l16 in enumerate(o16[b][1]):
+            assert torch.equal(glens[c][:, b].long().cpu(), l16[:, 0].long().cpu()), (b, c, glens[c][:, b], l16[:, 0])
+    _report(dict(config=f"second user turn (40 tokens over the ragged cache), B={B}", preset="llava-1.5-7b", dtype="bfloat16", B=B,
+                 err_vs_oracle_fp32=worst["err32"], oracle_floor_bf16_vs_fp32=worst["floor"], logit_scale=worst["scale"], kv_len_exact=True,
+                 worst_call=worst.get("call"), calls="prefill, 3 decode, 40-token turn, 2 decode"))
