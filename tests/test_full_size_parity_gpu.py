@@ -331,3 +331,68 @@ def test_full_size_7b_second_user_turn_vs_oracle(B):
     _report(dict(config=f"second user turn (40 tokens over the ragged cache), B={B}", preset="llava-1.5-7b", dtype="bfloat16", B=B,
                  err_vs_oracle_fp32=worst["err32"], oracle_floor_bf16_vs_fp32=worst["floor"], logit_scale=worst["scale"], kv_len_exact=True,
                  worst_call=worst.get("call"), calls="prefill, 3 decode, 40-token turn, 2 decode"))
+
+
+@pytest.mark.timeout(900)
+def test_full_size_7b_no_kv_cache_output_thinning_vs_oracle():
+    """use_cache=False at full 7B size (dynamic_modeling_llama.py:2393-2504; the loop of
+    bench_test/dynamic_llava_long_text_time_with_no_cache.py:336-349): B = 4 (the script's default), the id sequence grows by one
+    teacher token per call and the generated span is really thinned — the output predictor's logits are replaced on both sides by seeded
+    patterns with distinct channel-0 scores and different keep counts per sample (forward hook on our module, `forced_output_logits` in
+    the oracle), the image mask is the oracle's.  Per call: sequence length and kept output indices exact, last-position logits within
+    2 * floor + 1e-2 * scale of the fp32 oracle."""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    dev = torch.device("cuda")
+    cfgd = preset("llava-1.5-7b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = True
+    sd16 = device_state_dict(cfgd, seed=0, device=dev)
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device=dev)
+    model.get_vision_tower().load_model()
+    model.load_state_dict(sd16, strict=True)
+    B, T, n_calls = 4, 32, 10
+    ids, pix = synthetic_inputs(cfgd, B, T, seed=1)
+    ids, pix = ids.to(dev), pix.to(dev)
+    rng = torch.Generator().manual_seed(13)
+    forced = {}
+    for n in range(1, n_calls + 2):  # keyed by the predictor's input length, like oracle/gen_golden.py:nocache_forced_logits
+        z = torch.zeros(B, n, 2)
+        for b in range(B):
+            z[b, :, 0] = (torch.randperm(n, generator=rng).float() - (n - 1) / 2.0 + (0.75 if b % 2 else -0.75)) * 0.25
+        forced[n] = z.to(dev)
+    teacher = torch.randint(3, cfgd["vocab_size"], (B, n_calls), generator=torch.Generator().manual_seed(5)).to(dev)
+    rec0 = {}
+    O.model_forward(sd16, cfgd, ids, images=pix, record=rec0)
+    keep = rec0["keep_index"]
+    kw = dict(forced_output_logits=forced, forced_keep_index=keep, teacher_tokens=teacher)
+    o16 = O.nocache_loop(sd16, cfgd, ids, pix, n_calls, **kw)
+
+    def hook(mod, args, out):
+        return forced[args[0].shape[1]].to(out.dtype).reshape(out.shape)
+    h = model.model.output_text_score_predictor.register_forward_hook(hook)
+    model.model.answer_indice = None
+    total, got, lens, kept = ids.clone(), [], [], []
+    for t in range(n_calls):
+        rec = {}
+        out = model(total, images=pix, use_cache=False, forced_keep_index=keep, record=rec)
+        got.append(out.logits[:, -1].float().clone())
+        lens.append(out.logits.shape[1])
+        kept.append(rec.get("output_keep_index"))
+        total = torch.cat([total, teacher[:, t: t + 1]], dim=1)
+        del out
+    h.remove()
+    assert model.model.answer_indice == o16["answer_indice"]
+    del model
+    torch.cuda.empty_cache()
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    o32 = O.nocache_loop(sd32, cfgd, ids, pix.float(), n_calls, **kw)
+    assert lens == o16["seq_lens"], (lens, o16["seq_lens"])
+    assert o16["seq_lens"][-1] < o16["answer_indice"] + n_calls - 1  # tokens really left the sequence
+    for t in range(n_calls):
+        if o16["output_keep_index"][t].shape[1]:
+            assert torch.equal(kept[t].cpu(), o16["output_keep_index"][t].cpu()), t
+    floor = (o16["last_logits"].float() - o32["last_logits"]).abs().max().item()
+    scale = o32["last_logits"].abs().max().item()
+    err = (torch.stack(got, 0) - o32["last_logits"]).abs().max().item()
+    _report(dict(config=f"no KV cache, output thinning, B={B}, {n_calls} calls", preset="llava-1.5-7b", dtype="bfloat16", B=B,
+                 err_vs_oracle_fp32=err, oracle_floor_bf16_vs_fp32=floor, logit_scale=scale, seq_lens=lens))
+    assert err <= 2 * floor + 1e-2 * scale, (err, floor, scale)
