@@ -396,3 +396,106 @@ def test_full_size_7b_no_kv_cache_output_thinning_vs_oracle():
     _report(dict(config=f"no KV cache, output thinning, B={B}, {n_calls} calls", preset="llava-1.5-7b", dtype="bfloat16", B=B,
                  err_vs_oracle_fp32=err, oracle_floor_bf16_vs_fp32=floor, logit_scale=scale, seq_lens=lens))
     assert err <= 2 * floor + 1e-2 * scale, (err, floor, scale)
+
+
+@pytest.mark.timeout(900)
+def test_full_size_7b_instruct_predictor_vs_oracle():
+    """use_instruct_predictor=True at full 7B size, B = 1 (the reference asserts B == 1 for this stage): instruction tokens dropped at the
+    sparse layer during the prefill (dynamic_modeling_llama.py:2261-2375), then a 40-token new user turn whose K/V rows are persisted per
+    token in layers >= sparse_layer (:2506-2521, cache_utils.py:165-241), with decode steps before and after.  The instruct predictor's
+    own logits are compared with the oracle's, then its decisions are pinned to seeded patterns on both sides (forward hook here,
+    `forced_instruct` in the oracle) so that a near-tie cannot fork the runs.  Logits of every call within 2 * floor + 1e-2 * scale of the
+    fp32 oracle, kv_len exact after every call."""
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    dev = torch.device("cuda")
+    cfgd = preset("llava-1.5-7b")
+    cfgd["sparse_config"]["use_output_text_predictor"] = True
+    cfgd["sparse_config"]["use_instruct_predictor"] = True
+    sd16 = device_state_dict(cfgd, seed=0, device=dev)
+    model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device=dev)
+    model.get_vision_tower().load_model()
+    model.load_state_dict(sd16, strict=True)
+    T, Tc = 48, 40
+    ids, pix = synthetic_inputs(cfgd, 1, T, seed=1)
+    cont, _ = synthetic_inputs(cfgd, 1, Tc + 1, seed=5)
+    ids, pix, cont = ids.to(dev), pix.to(dev), cont[:, 1:].to(dev).clone()
+    cont[cont < 0] = 7
+    n_instr = T - 1 - 5 - 1  # the ids after the placeholder except the last one (scored span [a, b - 1), :2261-2375)
+    gen = torch.Generator().manual_seed(21)
+    decs = [torch.rand(1, n_instr, generator=gen) < 0.6, torch.rand(1, Tc, generator=gen) < 0.5]
+    decs = [d.to(dev) for d in decs]
+    out_dec = forced_text_decisions(5, 1, keep_rate=0.5, seed=11).to(dev)
+
+    def oracle_calls(sd, pixels, keep=None, teacher=None, record=None):
+        rec = {}
+        lg, past = O.model_forward(sd, cfgd, ids, images=pixels, forced_keep_index=keep, forced_instruct=decs[0], record=rec)
+        outs, lens, toks, step = [lg[:, -1]], [torch.stack(list(past[1]), 0).clone()], [], 0
+        rec1 = {}
+        for phase, n in (("dec", 3), ("turn", 1), ("dec", 2)):
+            for _ in range(n):
+                if phase == "turn":
+                    lg, past = O.model_forward(sd, cfgd, cont, past=past, forced_instruct=decs[1], record=rec1)
+                    outs.append(lg[0])
+                else:
+                    nxt = outs[-1][-1:].argmax(-1).reshape(1, 1) if teacher is None else teacher[len(toks)].reshape(1, 1)
+                    toks.append(nxt.reshape(()))
+                    lg, past = O.model_forward(sd, cfgd, nxt, past=past, forced_text_decision=out_dec[step].reshape(1, 1))
+                    outs.append(lg[:, -1])
+                    step += 1
+                lens.append(torch.stack(list(past[1]), 0).clone())
+        if record is not None:
+            record.update(prefill=rec.get("instruct_logits"), turn=rec1.get("instruct_logits"))
+        return outs, lens, toks, rec["keep_index"]
+
+    nat = {}
+    o16 = oracle_calls(sd16, pix, record=nat)
+    keep, toks = o16[3], torch.stack(o16[2]).reshape(1, -1)
+    seen = []
+
+    def hook(mod, args, out):
+        seen.append(out.detach().float().clone())
+        d = decs[len(seen) - 1]
+        z = torch.zeros_like(out)
+        z[..., 0] = torch.where(d.reshape(out.shape[:-1]), 1.0, -1.0).to(out.dtype)
+        return z
+    h = model.model.instruct_score_predictor.register_forward_hook(hook)
+    out = model(ids, images=pix, forced_keep_index=keep)
+    got, glens = [out.logits[:, -1].float().clone()], [torch.stack(list(out.past_key_values[1]), 0).clone()]
+    past, step = out.past_key_values, 0
+    for phase, n in (("dec", 3), ("turn", 1), ("dec", 2)):
+        for _ in range(n):
+            if phase == "turn":
+                out = model(cont, past_key_values=past)
+                got.append(out.logits[0].float().clone())
+            else:
+                out = model(toks[:, step: step + 1], past_key_values=past, forced_text_decision=out_dec[step])
+                got.append(out.logits[:, -1].float().clone())
+                step += 1
+            past = out.past_key_values
+            glens.append(torch.stack(list(past[1]), 0).clone())
+    h.remove()
+    assert len(seen) == 2
+    for mine, ref in zip(seen, (nat["prefill"], nat["turn"])):  # the predictor's own logits, before the hook pins the decisions
+        ref = ref.float().reshape(mine.shape)
+        assert (mine - ref).abs().max().item() < 0.03 * max(1.0, ref.abs().max().item())
+    del model, out, past
+    torch.cuda.empty_cache()
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    o32 = oracle_calls(sd32, pix.float(), keep=keep, teacher=toks[0])
+    worst = dict(err32=0.0, floor=0.0, scale=0.0)
+    for c, (a16, a32) in enumerate(zip(o16[0], o32[0])):
+        g = got[c]
+        a16, a32 = a16.float().reshape(g.shape), a32.float().reshape(g.shape)
+        floor, scale = (a16 - a32).abs().max().item(), a32.abs().max().item()
+        err = (g - a32).abs().max().item()
+        assert err <= 2 * floor + 1e-2 * scale, (c, err, floor, scale)
+        if err > worst["err32"]:
+            worst = dict(err32=err, floor=floor, scale=scale, call=c)
+    for c, l16 in enumerate(o16[1]):
+        assert torch.equal(glens[c].long().cpu(), l16.long().cpu()), (c, glens[c].flatten().tolist(), l16.flatten().tolist())
+    SL = cfgd["sparse_config"]["sparse_layer"]
+    assert int(o16[1][0][SL, 0]) < int(o16[1][0][0, 0]) - (576 - 115)  # instruction tokens really left the upper layers
+    _report(dict(config="instruct predictor: prefill drop + 40-token new turn, B=1", preset="llava-1.5-7b", dtype="bfloat16", B=1,
+                 err_vs_oracle_fp32=worst["err32"], oracle_floor_bf16_vs_fp32=worst["floor"], logit_scale=worst["scale"], kv_len_exact=True,
+                 worst_call=worst.get("call"), kv_len_after_prefill=[int(o16[1][0][0, 0]), int(o16[1][0][SL, 0])],
+                 kv_len_final=[int(o16[1][-1][0, 0]), int(o16[1][-1][SL, 0])]))
