@@ -244,6 +244,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
   } else {
     // ------------------------------------------------ epilogue (both CTAs) ------------------------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // The stream-K workspace is shared by every dl_linear launch of the stream, and this kernel is launched with programmatic
+    // serialization: its CTAs can be resident while the PREVIOUS GEMM's pairs are still parking and gathering through the same slots
+    // and flags.  Every warp that touches global memory on its own initiative must therefore execute griddepcontrol.wait itself —
+    // the producer's wait orders only what depends on its TMA loads.  (Round 2 bug: a tile finisher polled the flags before anything
+    // ordered it behind the producer's wait and consumed the previous launch's flags; profiles/r2_stream_k_workspace_race.md.)
+    pdl_wait();
     const int ew = warp - 4;
     const int q = warp & 3;   // TMEM lane quarter of this warp = rows [32q, 32q+32) of this CTA's half tile
     const int hh = ew >> 2;   // which of the two warps of the quarter: takes the 64-column chunks c with c % 2 == hh
@@ -287,15 +293,10 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
       }
 
       const bool gather = kb1 < KB;  // the tile's remaining k-blocks were computed (first thing) by the following pairs
-      // The workspace is shared by every dl_linear launch of the stream, and this kernel is launched with programmatic
-      // serialization: its CTAs can be resident while the PREVIOUS GEMM's pairs are still parking and gathering through the same
-      // slots and flags.  Only the producer thread executes griddepcontrol.wait, so nothing of the workspace may be touched before
-      // this warp has observed its own accumulator (tmem_full <- MMA <- TMA <- the producer's wait): polling the flags first let an
-      // early-resident finisher consume the previous launch's flags (wrong sums on shapes where both launches are cut, e.g. M = 292).
-      mbar_wait(&S.tmem_full[a], (sc >> 1) & 1);
-      tc_fence_after();
       if (gather) {
-        // wait until this warp's counterpart in every contributing pair has parked its slice
+        // wait until this warp's counterpart in every contributing pair has parked its slice: polled BEFORE this warp's own accumulator
+        // is waited for, so the flag round trips through L2 hide under the pair's main loop.  Safe only because this warp executed
+        // griddepcontrol.wait itself (top of the epilogue branch): the workspace is quiescent, see there.
         if (lane == 0) {
           const int tile_end = (skt + 1) * KB;
           for (int p2 = pair + 1;; ++p2) {
@@ -307,6 +308,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const __grid_const
         }
         __syncwarp();
       }
+      mbar_wait(&S.tmem_full[a], (sc >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = hh; c < OUT_W / 64; c += 2) {
         const int col0 = col_t + c * 64;
