@@ -20,7 +20,7 @@ from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
 from dynamic_llava_b200.presets import preset
 from dynamic_llava_b200.synthetic import device_state_dict, synthetic_inputs
 dev = torch.device("cuda")
-cfgd = preset("llava-1.5-7b")
+cfgd = preset(os.environ.get("PDL_BITWISE_PRESET", "llava-1.5-7b"))
 cfgd["sparse_config"]["use_output_text_predictor"] = False
 model = DynamicLlavaLlamaForCausalLM(DynamicLlavaConfig(**cfgd), device=dev)
 model.get_vision_tower().load_model()
