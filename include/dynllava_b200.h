@@ -72,7 +72,9 @@ int dl_drop_cls(const void* x, void* out, int B, int NP, int C, cudaStream_t str
  * bias / residual may be NULL.  K % 64 == 0, N % 8 == 0.  x, w, out contiguous row-major.
  * workspace (or NULL): dl_linear_workspace_bytes() bytes of device memory, ZEROED once by the caller and then owned by the calls of
  * one stream: enables stream-K work distribution (equal (tile, k-block) ranges per CTA pair; partial accumulators of split tiles are
- * parked there and added in fixed order: deterministic); every launch leaves it zeroed again.  NULL: whole tiles per pair. */
+ * parked there and added in fixed order: deterministic); every launch leaves it zeroed again.  NULL: whole tiles per pair.
+ * Launched with programmatic stream serialization: consecutive launches of the stream overlap their prologue with the predecessor's
+ * tail and may share the workspace (each warp that touches it waits for the predecessor grid first); two STREAMS must not share one. */
 int64_t dl_linear_workspace_bytes(void);
 int dl_linear(const void* x, const void* w, const void* bias, const void* residual, void* out, int M, int N, int K, int act,
               void* workspace, cudaStream_t stream);
