@@ -113,3 +113,111 @@ def test_random_case_against_oracle(seed):
         assert torch.equal(lens, o16["true_len"]), (lens, o16["true_len"], c)
     else:
         assert (lens[SL:] <= P - 16 + k + n_new - 1).all() and (lens[SL:] >= P - 16 + k).all(), (lens, c)
+
+
+def _instr_model(wseed):
+    from dynamic_llava_b200 import DynamicLlavaConfig, DynamicLlavaLlamaForCausalLM
+    key = ("instr", wseed)
+    if key not in _MODELS:
+        c = preset("toy")
+        c["sparse_config"]["use_output_text_predictor"] = True
+        c["sparse_config"]["use_instruct_predictor"] = True
+        sd32 = numpy_state_dict(c, seed=wseed)
+        sd16 = {k: v.to(BF) for k, v in sd32.items()}
+        _MODELS[key] = (DynamicLlavaLlamaForCausalLM.from_state_dict(DynamicLlavaConfig(**c), sd16, device="cuda", dtype=BF), sd32, sd16)
+    return _MODELS[key]
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_random_multi_turn_case_against_oracle(seed):
+    """seeded random multi-round conversations (model_lvis_multi_round_for_meteor.py:150-185): prefill, a few decode steps, a new user
+    turn of 2-24 ids over the ragged cache, more decode steps, sometimes a second new turn; with the instruct predictor (B = 1, its
+    decisions pinned on both sides to seeded patterns: prefill drop and per-token persistence) or without (B = 1-3, ragged default, each
+    sample against itself run alone).  Every call's logits within 2 * floor + 1e-2 * scale of the fp32 oracle, KV lengths exact."""
+    r = np.random.Generator(np.random.PCG64(7000 + seed))
+    instr = bool(r.integers(0, 2))
+    B = 1 if instr else int(r.integers(1, 4))
+    T = int(r.integers(8, 41))
+    image_pos = int(r.integers(1, T - 3))  # leave >= 2 instruct ids so the scored span [a, b - 1) is not empty
+    rate = float(r.choice([0.2, 0.5, 1.0]))
+    wseed = int(r.integers(0, 3))
+    plan = [("dec", int(r.integers(1, 4))), ("turn", int(r.integers(2, 25))), ("dec", int(r.integers(1, 4)))]
+    if r.integers(0, 2):
+        plan += [("turn", int(r.integers(2, 25))), ("dec", int(r.integers(1, 3)))]
+    cfg = preset("toy")
+    cfg["sparse_config"].update(vision_keep_rate=rate, use_output_text_predictor=True, use_instruct_predictor=instr)
+    model, sd32, sd16 = _instr_model(wseed) if instr else _model(cfg, wseed)
+    model.config.sparse_config.update(vision_keep_rate=rate, use_output_text_predictor=True, use_instruct_predictor=instr)
+    model.config.reference_batched_quirk = False
+    ids, pix = synthetic_inputs(cfg, B, T, seed=int(r.integers(1, 100)), image_pos=image_pos, dtype=BF)
+    g = torch.Generator().manual_seed(seed)
+    turns = [torch.randint(3, cfg["vocab_size"], (B, n), generator=g) for kind, n in plan if kind == "turn"]
+    n_dec = sum(n for kind, n in plan if kind == "dec")
+    dec = torch.rand(n_dec, B, generator=g) < 0.5
+    n_instr = T - 1 - image_pos - 1
+    idecs = [torch.rand(1, n_instr, generator=g) < 0.6] + [torch.rand(1, t.shape[1], generator=g) < 0.5 for t in turns]
+
+    def oracle_calls(sd, pixels, b, keep=None, teacher=None):
+        rec = {}
+        lg, past = O.model_forward(sd, cfg, ids[b: b + 1], images=pixels[b: b + 1], forced_keep_index=keep, record=rec,
+                                   forced_instruct=idecs[0] if instr else None)
+        outs, lens, toks, step, ti = [lg[:, -1]], [torch.stack(list(past[1]), 0).clone()], [], 0, 0
+        for kind, n in plan:
+            if kind == "turn":
+                lg, past = O.model_forward(sd, cfg, turns[ti][b: b + 1], past=past, forced_instruct=idecs[1 + ti] if instr else None)
+                outs.append(lg[0]); lens.append(torch.stack(list(past[1]), 0).clone())
+                ti += 1
+                continue
+            for _ in range(n):
+                nxt = outs[-1][-1:].argmax(-1).reshape(1, 1) if teacher is None else teacher[len(toks)].reshape(1, 1)
+                toks.append(nxt.reshape(()))
+                lg, past = O.model_forward(sd, cfg, nxt, past=past, forced_text_decision=dec[step, b].reshape(1, 1))
+                outs.append(lg[:, -1]); lens.append(torch.stack(list(past[1]), 0).clone())
+                step += 1
+        return outs, lens, toks, rec["keep_index"]
+
+    o16 = [oracle_calls(sd16, pix, b) for b in range(B)]
+    keep = torch.cat([o[3] for o in o16], 0)
+    toks = torch.stack([torch.stack(o[2]) for o in o16], 0)
+    seen = []
+
+    def hook(mod, args, out):
+        d = idecs[len(seen)].to(out.device)
+        seen.append(1)
+        z = torch.zeros_like(out)
+        z[..., 0] = torch.where(d.reshape(out.shape[:-1]), 1.0, -1.0).to(out.dtype)
+        return z
+    h = model.model.instruct_score_predictor.register_forward_hook(hook) if instr else None
+    try:
+        out = model(ids.cuda(), images=pix.cuda(), forced_keep_index=keep)
+        got, glens = [out.logits[:, -1].float().cpu()], [torch.stack(list(out.past_key_values[1]), 0).cpu()]
+        past, step, ti = out.past_key_values, 0, 0
+        for kind, n in plan:
+            if kind == "turn":
+                out = model(turns[ti].cuda(), past_key_values=past)
+                got.append(out.logits.float().cpu())
+                ti += 1
+                past = out.past_key_values
+                glens.append(torch.stack(list(past[1]), 0).cpu())
+                continue
+            for _ in range(n):
+                out = model(toks[:, step: step + 1].cuda(), past_key_values=past, forced_text_decision=dec[step])
+                got.append(out.logits[:, -1].float().cpu())
+                step += 1
+                past = out.past_key_values
+                glens.append(torch.stack(list(past[1]), 0).cpu())
+    finally:
+        if h is not None:
+            h.remove()
+    if instr:
+        assert len(seen) == 1 + len(turns)
+    del out, past
+    for b in range(B):
+        o32 = oracle_calls(sd32, pix.float(), b, keep=keep[b: b + 1], teacher=toks[b])
+        for c, (a16, a32) in enumerate(zip(o16[b][0], o32[0])):
+            gg = got[c][b]
+            a16, a32 = a16.float().reshape(gg.shape), a32.float().reshape(gg.shape)
+            floor, scale = (a16 - a32).abs().max().item(), a32.abs().max().item()
+            assert (gg - a32).abs().max().item() <= 2 * floor + 1e-2 * scale, (b, c, plan, instr)
+        for c, l16 in enumerate(o16[b][1]):
+            assert torch.equal(glens[c][:, b].long(), l16[:, 0].long()), (b, c, glens[c][:, b], l16[:, 0], plan, instr)
