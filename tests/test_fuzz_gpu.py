@@ -221,3 +221,57 @@ def test_random_multi_turn_case_against_oracle(seed):
             assert (gg - a32).abs().max().item() <= 2 * floor + 1e-2 * scale, (b, c, plan, instr)
         for c, l16 in enumerate(o16[b][1]):
             assert torch.equal(glens[c][:, b].long(), l16[:, 0].long()), (b, c, glens[c][:, b], l16[:, 0], plan, instr)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_no_kv_cache_case_against_oracle(seed):
+    """seeded random runs of the no-KV-cache mode (use_cache=False; bench_test/dynamic_llava_long_text_time_with_no_cache.py:336-349): batch
+    1-4, prompt 6-40 ids, 3-14 calls, the output predictor's logits pinned on both sides to seeded patterns with different keep counts per
+    sample (so the batch-max padding of the kept set is exercised).  Sequence lengths and kept indices exact, last-position logits within
+    2 * floor + 1e-2 * scale of the fp32 oracle."""
+    r = np.random.Generator(np.random.PCG64(9000 + seed))
+    B, T, n_calls = int(r.integers(1, 5)), int(r.integers(6, 41)), int(r.integers(3, 15))
+    image_pos = int(r.integers(1, T - 1))
+    rate = float(r.choice([0.2, 0.5, 1.0]))
+    wseed = int(r.integers(0, 3))
+    cfg = preset("toy")
+    cfg["sparse_config"].update(vision_keep_rate=rate, use_output_text_predictor=True)
+    model, sd32, sd16 = _model(cfg, wseed)
+    model.config.sparse_config.update(vision_keep_rate=rate, use_output_text_predictor=True, use_instruct_predictor=False)
+    ids, pix = synthetic_inputs(cfg, B, T, seed=int(r.integers(1, 100)), image_pos=image_pos, dtype=BF)
+    g = torch.Generator().manual_seed(seed)
+    forced = {}
+    for n in range(1, n_calls + 2):
+        z = torch.zeros(B, n, 2)
+        for b in range(B):
+            z[b, :, 0] = (torch.randperm(n, generator=g).float() - (n - 1) / 2.0 + float(torch.randn((), generator=g))) * 0.25
+        forced[n] = z
+    teacher = torch.randint(3, cfg["vocab_size"], (B, n_calls), generator=g)
+    rec0 = {}
+    O.model_forward(sd16, cfg, ids, images=pix, record=rec0)
+    keep = rec0["keep_index"]
+    kw = dict(forced_output_logits=forced, forced_keep_index=keep, teacher_tokens=teacher)
+    o16 = O.nocache_loop(sd16, cfg, ids, pix, n_calls, **kw)
+    o32 = O.nocache_loop(sd32, cfg, ids, pix.float(), n_calls, **kw)
+
+    def hook(mod, args, out):
+        return forced[args[0].shape[1]].to(out.device, out.dtype).reshape(out.shape)
+    h = model.model.output_text_score_predictor.register_forward_hook(hook)
+    model.model.answer_indice = None
+    try:
+        total, got = ids.clone(), []
+        for t in range(n_calls):
+            rec = {}
+            out = model(total.cuda(), images=pix.cuda(), use_cache=False, forced_keep_index=keep, record=rec)
+            assert out.logits.shape[1] == o16["seq_lens"][t], (t, out.logits.shape, o16["seq_lens"])
+            if o16["output_keep_index"][t].shape[1]:
+                assert torch.equal(rec["output_keep_index"].cpu(), o16["output_keep_index"][t]), t
+            got.append(out.logits[:, -1].float().cpu())
+            total = torch.cat([total, teacher[:, t: t + 1]], dim=1)
+    finally:
+        h.remove()
+    assert model.model.answer_indice == o16["answer_indice"]
+    model.model.answer_indice = None
+    floor = (o16["last_logits"].float() - o32["last_logits"]).abs().max().item()
+    scale = o32["last_logits"].abs().max().item()
+    assert (torch.stack(got, 0) - o32["last_logits"]).abs().max().item() <= 2 * floor + 1e-2 * scale
